@@ -1,0 +1,210 @@
+/*
+ * misob200.h — C ABI of libmisob200.so: the B200 (sm_100a) implementation of the detection
+ * post-processing + region-feature hot path behind miso's torchvision Faster/Mask R-CNN
+ * pipelines (microfossil/particle-object-detection).
+ *
+ * Citations: `ref:` = the reference repo, `tv:` = torchvision 0.26.0 Python layer (the
+ * third-party code the reference calls), `tv-csrc:` = torchvision native sources (dispatcher
+ * registration sites). Each entry point names the reference interface it
+ * replaces. INTEGRATION.md shows the reference-side binding (ctypes) for every symbol.
+ *
+ * Conventions:
+ *  - every pointer is a DEVICE pointer unless the name ends in _host or the comment says so;
+ *  - the caller owns all memory including the workspace; the library never allocates,
+ *    frees or synchronises; all work is enqueued on `stream`;
+ *  - return value: MB_OK, a negative MB_ERR_* argument error, or a positive cudaError_t;
+ *  - data-dependent counts are written to device memory;
+ *  - fp32 boxes are (x1, y1, x2, y2); indices are int64 where torchvision returns int64.
+ */
+#ifndef MISOB200_H
+#define MISOB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_ABI_VERSION 1
+
+#define MB_OK 0
+#define MB_ERR_INVALID_ARG (-1)
+#define MB_ERR_WORKSPACE (-2)   /* workspace too small */
+#define MB_ERR_UNSUPPORTED (-3) /* configuration outside the implemented envelope */
+
+#define MB_MAX_LEVELS 8
+#define MB_MAX_ANCHORS_PER_LOC 16
+#define MB_MAX_IMAGES 64
+
+typedef struct CUstream_st* mb_stream_t;
+
+int mb_abi_version(void);
+/* "sm_100a;<kernel list>" — lets the host assert the CUDA build is the one loaded */
+const char* mb_build_info(void);
+
+/* ------------------------------------------------------------------------------------
+ * Non-maximum suppression.
+ * Replaces torchvision::nms (tv:ops/boxes.py:20-48 -> tv-csrc:ops/cuda/nms_kernel.cu:204,
+ * semantics of the CPU kernel tv-csrc:ops/cpu/nms_kernel.cpp:116) and both batched_nms
+ * strategies (tv:ops/boxes.py:86-120).
+ *   mode 0  plain nms (groups ignored)
+ *   mode 1  per-group NMS on raw coordinates ("vanilla"); groups[i] in [0, num_groups)
+ *   mode 2  coordinate trick: boxes + fl(fl(group) * fl(max(boxes) + 1)), then plain nms
+ * keep_out [num_boxes] receives original indices in descending-score order (ties: lower
+ * index first). status_out[0] = number kept, or -1 if the mask workspace was too small, in
+ * which case status_out[1] = mask words (8 bytes each) required; status_out has 4 int64.
+ * ------------------------------------------------------------------------------------ */
+#define MB_NMS_PLAIN 0
+#define MB_NMS_VANILLA 1
+#define MB_NMS_TRICK 2
+size_t mb_nms_workspace_bytes(int64_t num_boxes, int32_t num_groups);
+int mb_nms(const float* boxes, const float* scores, const int64_t* groups, int64_t num_boxes,
+           int32_t num_groups, int32_t mode, double iou_threshold, int64_t* keep_out,
+           int64_t* status_out, void* workspace, size_t workspace_bytes, void* mask_workspace,
+           size_t mask_workspace_bytes, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * RoIAlign.
+ * mb_roi_align replaces torchvision::roi_align forward (tv:ops/roi_align.py:203-260 ->
+ * tv-csrc:ops/cuda/roi_align_kernel.cu:470; arithmetic of the CPU kernel
+ * tv-csrc:ops/cpu/roi_align_kernel.cpp:393): input NCHW fp32, rois [K,5] =
+ * (batch, x1, y1, x2, y2), out [K, C, PH, PW].
+ * mb_multiscale_roi_align replaces MultiScaleRoIAlign.forward's per-level loop
+ * (tv:ops/poolers.py:147-227) in ONE launch: level assignment (LevelMapper, :73-84) is
+ * evaluated on the device as area thresholds derived by the host from the mapper, every
+ * output element is written exactly once. level_thresholds[i] = smallest fp32 box area
+ * mapped to level > i (num_levels-1 entries, ascending).
+ * exact != 0 reproduces the CPU kernel's operation order bit for bit (no FMA contraction).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_levels;
+    int32_t num_images;
+    int32_t channels;
+    int32_t pooled_h, pooled_w;
+    int32_t sampling_ratio;
+    int32_t aligned;
+    int32_t exact;
+    int32_t height[MB_MAX_LEVELS], width[MB_MAX_LEVELS];
+    float spatial_scale[MB_MAX_LEVELS];
+    float level_thresholds[MB_MAX_LEVELS];
+    const float* features[MB_MAX_LEVELS]; /* device, NCHW contiguous */
+} mb_roi_align_params;
+size_t mb_roi_align_workspace_bytes(int64_t num_rois);
+int mb_multiscale_roi_align(const mb_roi_align_params* params_host, const float* rois, int64_t num_rois,
+                            float* out, int32_t* levels_out /* nullable, [K] */, void* workspace,
+                            size_t workspace_bytes, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Element-wise box operators.
+ *  mb_box_decode      BoxCoder.decode_single (tv:models/detection/_utils.py:183-224):
+ *                     rel_codes [M, 4*C], boxes [M,4] -> out [M, C, 4]
+ *  mb_clip_boxes      clip_boxes_to_image (tv:ops/boxes.py:149-182)
+ *  mb_box_convert     box_convert for xyxy/xywh/cxcywh (tv:ops/boxes.py:185-270); fmt 0/1/2
+ *  mb_remove_small    remove_small_boxes (tv:ops/boxes.py:123-146): ascending indices, count
+ *  mb_resize_boxes    resize_boxes (tv:models/detection/transform.py:306-319)
+ *  mb_grid_anchors    AnchorGenerator.grid_anchors for one level (tv:.../anchor_utils.py:84-113)
+ * ------------------------------------------------------------------------------------ */
+int mb_box_decode(const float* rel_codes, const float* boxes, int64_t num_boxes, int32_t num_classes,
+                  float wx, float wy, float ww, float wh, float bbox_xform_clip, float* out,
+                  mb_stream_t stream);
+int mb_clip_boxes(const float* boxes, int64_t num_boxes, float height, float width, float* out,
+                  mb_stream_t stream);
+int mb_box_convert(const float* boxes, int64_t num_boxes, int32_t in_fmt, int32_t out_fmt, float* out,
+                   mb_stream_t stream);
+int mb_remove_small(const float* boxes, int64_t num_boxes, float min_size, int64_t* keep_out,
+                    int64_t* count_out, mb_stream_t stream);
+int mb_resize_boxes(const float* boxes, int64_t num_boxes, float ratio_h, float ratio_w, float* out,
+                    mb_stream_t stream);
+int mb_grid_anchors(const float* base_anchors_host, int32_t num_base, int32_t grid_h, int32_t grid_w,
+                    int32_t stride_h, int32_t stride_w, float* out, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused RPN post-head stage: anchors + per-level top-k + decode + clip + small-box and
+ * score filter + per-level NMS + post-NMS top-n, straight from the head's NCHW outputs.
+ * Replaces AnchorGenerator.forward, concat_box_prediction_layers, BoxCoder.decode and
+ * RegionProposalNetwork.filter_proposals (tv:models/detection/anchor_utils.py:115-133,
+ * rpn.py:81-110, _utils.py:162-224, rpn.py:231-297).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_images, num_levels;
+    int32_t feat_h[MB_MAX_LEVELS], feat_w[MB_MAX_LEVELS];
+    int32_t stride_h[MB_MAX_LEVELS], stride_w[MB_MAX_LEVELS];
+    int32_t anchors_per_loc[MB_MAX_LEVELS];
+    float base_anchors[MB_MAX_LEVELS][MB_MAX_ANCHORS_PER_LOC][4];
+    int32_t image_h[MB_MAX_IMAGES], image_w[MB_MAX_IMAGES]; /* images.image_sizes (pre-padding) */
+    int32_t pre_nms_top_n, post_nms_top_n;
+    double nms_thresh;
+    float score_thresh, min_size;
+    float wx, wy, ww, wh, bbox_xform_clip;
+    int64_t trick_numel; /* batched_nms strategy rule (tv:ops/boxes.py:80): 4000 cpu, 100000 cuda, -1 vanilla */
+    const float* objectness[MB_MAX_LEVELS]; /* [N, A, H, W] logits */
+    const float* deltas[MB_MAX_LEVELS];     /* [N, 4A, H, W] */
+} mb_rpn_params;
+size_t mb_rpn_workspace_bytes(const mb_rpn_params* params_host);
+/* proposals_out [N, post_nms_top_n, 4], scores_out [N, post_nms_top_n], counts_out [N] int32.
+ * Optional debug outputs (nullable): topk_idx_out [N, sum_l min(pre, A_l)] int64 flattened
+ * anchor indices in the reference's (level, h, w, a) order. */
+int mb_rpn_proposals(const mb_rpn_params* params_host, float* proposals_out, float* scores_out,
+                     int32_t* counts_out, int64_t* topk_idx_out, void* workspace,
+                     size_t workspace_bytes, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Fused detection post-processing: softmax + decode + clip + score/small filters + per-class
+ * NMS + top detections_per_img + resize to the original image size.
+ * Replaces RoIHeads.postprocess_detections (tv:models/detection/roi_heads.py:680-737) and
+ * GeneralizedRCNNTransform.postprocess / resize_boxes (transform.py:257-277, :306-319).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_images, num_classes; /* classes incl. background */
+    int32_t max_props_per_image;     /* row capacity of proposals per image */
+    int32_t detections_per_img;
+    int32_t image_h[MB_MAX_IMAGES], image_w[MB_MAX_IMAGES]; /* resized (network) sizes */
+    int32_t orig_h[MB_MAX_IMAGES], orig_w[MB_MAX_IMAGES];   /* original sizes; 0 -> no resize */
+    double nms_thresh;
+    float score_thresh, min_size;
+    float wx, wy, ww, wh, bbox_xform_clip;
+    int64_t trick_numel;
+} mb_det_params;
+size_t mb_det_workspace_bytes(const mb_det_params* params_host);
+/* class_logits [sumR, C], box_regression [sumR, 4C], proposals [N, max_props, 4] with
+ * prop_counts [N] live rows each; logits/regression rows are packed in image order
+ * (row offset of image n = sum of earlier counts) when packed != 0, else strided by max_props.
+ * Outputs: det_boxes [N, dpi, 4] (original image scale), det_boxes_net [N, dpi, 4] (network
+ * scale, nullable), det_scores [N, dpi], det_labels [N, dpi] int64, det_counts [N] int32. */
+int mb_det_postprocess(const mb_det_params* params_host, const float* class_logits,
+                       const float* box_regression, const float* proposals, const int32_t* prop_counts,
+                       int32_t packed, float* det_boxes, float* det_boxes_net, float* det_scores,
+                       int64_t* det_labels, int32_t* det_counts, void* workspace, size_t workspace_bytes,
+                       mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Score filter + crop extraction.
+ * Replaces miso's `scores > threshold` filter and xyxy->xywh annotation
+ * (ref:miso/object_detection/inference.py:53-64), RectangleAnnotation.coords_int
+ * (ref:miso/object_detection/dataset/annotation.py:120-127) and the crop slice
+ * (ref:miso/object_detection/crop.py:28-30).
+ * mb_crop_plan: per image n, detections [N, cap, 4]/[N, cap] with det_counts[n] live rows;
+ *   writes, for every detection passing the filter (original order), rects [N*cap, 4] int32 =
+ *   (x_begin, y_begin, width, height) after numpy slice resolution, xywh [N*cap, 4] fp32,
+ *   src index [N*cap] int32 (n*cap + i), byte offsets [N*cap+1] int64 into the packed crop
+ *   buffer, and totals[0] = number of crops, totals[1] = total bytes.
+ * mb_crop_gather: copies the pixels. images: one uint8 HWC device pointer per image.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_images, capacity, channels;
+    int32_t image_h[MB_MAX_IMAGES], image_w[MB_MAX_IMAGES];
+    const uint8_t* images[MB_MAX_IMAGES]; /* device, HWC uint8, row pitch = w*channels */
+    float threshold;
+} mb_crop_params;
+int mb_crop_plan(const mb_crop_params* params_host, const float* det_boxes, const float* det_scores,
+                 const int32_t* det_counts, int32_t* rects_out, float* xywh_out, int32_t* src_out,
+                 int64_t* offsets_out, int64_t* totals_out, mb_stream_t stream);
+int mb_crop_gather(const mb_crop_params* params_host, const int32_t* rects, const int32_t* src,
+                   const int64_t* offsets, const int64_t* totals, uint8_t* crops_out,
+                   int64_t crops_capacity_bytes, mb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MISOB200_H */

@@ -1,0 +1,374 @@
+// nms_core.cuh — segmented greedy NMS building blocks shared by the generic
+// torchvision-signature entry points (nms.cu), the fused RPN path (rpn.cu) and the fused
+// detection path (detpost.cu).
+//
+// Reference semantics: torchvision::nms CPU (tv-csrc:ops/cpu/nms_kernel.cpp:116, restated in
+// SURVEY.md Appendix B.1): areas and IoU with one fp32 rounding per operation (no FMA),
+// suppression iff (double)iou > iou_threshold (strict), candidates visited in stable
+// descending-score order.
+//
+// Pipeline over "segments" (one segment = one independent NMS problem, e.g. image x level):
+//   rank    : order the elements of every segment by a unique 64-bit key (rank by counting)
+//   meta    : per-segment word counts, mask offsets and a tile prefix (single block scan)
+//   mask    : 64x64 IoU tiles -> one 64-bit suppression word per (row box, column block),
+//             upper-triangular tiles only, persistent grid sized from the SM count
+//   sweep   : one CTA per segment; serial 64-step resolve of the diagonal word, parallel OR
+//             of the kept rows into the removed[] bit-vector held in shared memory
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+struct SegArrays {
+    int* seg_start;        // [G]   first position of segment g in the sorted arrays
+    int* seg_count;        // [G]   number of live elements
+    int* seg_words;        // [G]   ceil(count/64)
+    long long* mask_off;   // [G]   word offset of the segment's mask rows
+    long long* tile_pre;   // [G+1] exclusive prefix of T(T+1)/2
+    int* keep_off;         // [G+1] exclusive prefix of T (word offset into keepbits)
+    int* seg_kept;         // [G]   number of boxes kept by the sweep
+    long long* totals;     // [4]   0: tiles, 1: mask words needed, 2: overflow flag, 3: spare
+};
+
+inline size_t seg_arrays_bytes(int G) {
+    size_t b = 0;
+    b += align_up(sizeof(int) * G, 256) * 4;              // start,count,words,kept
+    b += align_up(sizeof(long long) * G, 256);            // mask_off
+    b += align_up(sizeof(long long) * (G + 1), 256);      // tile_pre
+    b += align_up(sizeof(int) * (G + 1), 256);            // keep_off
+    b += 256;                                             // totals
+    return b + 256;
+}
+
+inline SegArrays carve_seg_arrays(Carver& c, int G) {
+    SegArrays s;
+    s.seg_start = c.take<int>(G);
+    s.seg_count = c.take<int>(G);
+    s.seg_words = c.take<int>(G);
+    s.seg_kept = c.take<int>(G);
+    s.mask_off = c.take<long long>(G);
+    s.tile_pre = c.take<long long>(G + 1);
+    s.keep_off = c.take<int>(G + 1);
+    s.totals = c.take<long long>(4);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------
+// block-wide exclusive scan of one long long per thread (1024 threads), returns total
+// ------------------------------------------------------------------------------------
+__device__ inline long long block_excl_scan_1024(long long v, long long* sh /*[1024+32]*/, long long& total) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sh[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        long long w = sh[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        sh[32 + lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    long long warp_base = wid ? sh[32 + wid - 1] : 0;
+    total = sh[32 + 31];
+    long long r = warp_base + x - v;
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------
+// meta: from seg_count (and, when compute_starts, a packed layout) derive everything else.
+// Also evaluates torchvision's batched_nms strategy rule per image for the fused paths
+// (tv:ops/boxes.py:80): trick iff 4*boxes_in_image <= trick_numel, offsets
+// fl(fl(group) * fl(max_coord + 1)) (tv:ops/boxes.py:99-102); 0 otherwise.
+// ------------------------------------------------------------------------------------
+struct MetaRule {
+    int segs_per_image;     // 0 -> no per-image rule (seg_offset not written)
+    int group_base;         // group value of the first segment of an image
+    long long trick_numel;  // numel threshold of the reference rule; <0 -> always vanilla
+    const float* img_max;   // [num_images] max coordinate over the image's live boxes
+    float* seg_offset;      // [G] out
+};
+
+__global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, int compute_starts,
+                                                   long long mask_cap_words, MetaRule rule) {
+    __shared__ long long sh[64];
+    __shared__ long long carry[4];
+    const int tid = threadIdx.x;
+    if (tid < 4) carry[tid] = 0;
+    __syncthreads();
+    for (int base = 0; base < G; base += 1024) {
+        const int g = base + tid;
+        const int n = g < G ? s.seg_count[g] : 0;
+        const long long T = (n + 63) >> 6;
+        long long tot;
+        long long st = block_excl_scan_1024(n, sh, tot);
+        const long long c0 = carry[0];
+        __syncthreads();
+        if (tid == 0) carry[0] = c0 + tot;
+        long long mo = block_excl_scan_1024((long long)n * T, sh, tot);
+        const long long c1 = carry[1];
+        __syncthreads();
+        if (tid == 0) carry[1] = c1 + tot;
+        long long tp = block_excl_scan_1024(T * (T + 1) / 2, sh, tot);
+        const long long c2 = carry[2];
+        __syncthreads();
+        if (tid == 0) carry[2] = c2 + tot;
+        long long ko = block_excl_scan_1024(T, sh, tot);
+        const long long c3 = carry[3];
+        __syncthreads();
+        if (tid == 0) carry[3] = c3 + tot;
+        if (g < G) {
+            if (compute_starts) s.seg_start[g] = (int)(c0 + st);
+            s.seg_words[g] = (int)T;
+            s.mask_off[g] = c1 + mo;
+            s.tile_pre[g] = c2 + tp;
+            s.keep_off[g] = (int)(c3 + ko);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        s.tile_pre[G] = carry[2];
+        s.keep_off[G] = (int)carry[3];
+        s.totals[0] = carry[2];
+        s.totals[1] = carry[1];
+        s.totals[2] = carry[1] > mask_cap_words ? 1 : 0;
+    }
+    if (rule.segs_per_image > 0) {
+        for (int g = tid; g < G; g += 1024) {
+            const int img = g / rule.segs_per_image;
+            long long cnt = 0;
+            for (int q = 0; q < rule.segs_per_image; ++q) cnt += s.seg_count[img * rule.segs_per_image + q];
+            float off = 0.0f;
+            if (rule.trick_numel >= 0 && 4 * cnt <= rule.trick_numel) {
+                const float grp = (float)(rule.group_base + g % rule.segs_per_image);
+                off = __fmul_rn(grp, __fadd_rn(rule.img_max[img], 1.0f));
+            }
+            rule.seg_offset[g] = off;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// rank by counting inside segments. Keys are unique 64-bit values (score key << 32 | tie).
+// Position p of the bucketed arrays belongs to segment bseg[p] (or -1 for a hole).
+// Writes skey/sbox at seg_start + rank; optional per-segment box offset (trick mode).
+// ------------------------------------------------------------------------------------
+constexpr int kRankThreads = 256;
+constexpr int kRankTile = 1024;
+
+__global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
+    const unsigned long long* __restrict__ bkey, const float4* __restrict__ bbox,
+    const int* __restrict__ bseg, const int* __restrict__ seg_start,
+    const int* __restrict__ seg_count, const float* __restrict__ seg_offset, int P,
+    unsigned long long* __restrict__ skey, float4* __restrict__ sbox) {
+    __shared__ unsigned long long tile[kRankTile];
+    __shared__ int s_lo, s_hi;
+    const int tid = threadIdx.x;
+    const int p = blockIdx.x * kRankThreads + tid;
+    int g = -1, lo = 0, hi = 0;
+    unsigned long long key = 0;
+    if (p < P) {
+        g = bseg[p];
+        if (g >= 0) { lo = seg_start[g]; hi = lo + seg_count[g]; key = bkey[p]; }
+    }
+    if (tid == 0) { s_lo = 0x7fffffff; s_hi = 0; }
+    __syncthreads();
+    if (g >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    __syncthreads();
+    const int ulo = s_lo, uhi = s_hi;
+    int rank = 0;
+    for (int t0 = ulo; t0 < uhi; t0 += kRankTile) {
+        const int tn = min(kRankTile, uhi - t0);
+        __syncthreads();
+        for (int j = tid; j < tn; j += kRankThreads) tile[j] = bkey[t0 + j];
+        __syncthreads();
+        const int a = max(lo, t0) - t0, b = min(hi, t0 + tn) - t0;
+        int cnt = 0;
+#pragma unroll 4
+        for (int j = a; j < b; ++j) cnt += (tile[j] < key) ? 1 : 0;
+        rank += cnt;
+    }
+    if (g >= 0) {
+        const int dst = lo + rank;
+        skey[dst] = key;
+        if (sbox != nullptr) {
+            float4 bx = bbox[p];
+            if (seg_offset != nullptr) {
+                const float o = seg_offset[g];
+                bx.x = __fadd_rn(bx.x, o); bx.y = __fadd_rn(bx.y, o);
+                bx.z = __fadd_rn(bx.z, o); bx.w = __fadd_rn(bx.w, o);
+            }
+            sbox[dst] = bx;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// IoU predicate with the reference's exact operation order.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ float box_area_rn(const float4 b) {
+    return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+
+__device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_a, const float4 b,
+                                               const float area_b, const float thr_up) {
+    const float xx1 = (a.x < b.x) ? b.x : a.x;   // std::max(a, b) == (a < b) ? b : a
+    const float yy1 = (a.y < b.y) ? b.y : a.y;
+    const float xx2 = (b.z < a.z) ? b.z : a.z;   // std::min(a, b) == (b < a) ? b : a
+    const float yy2 = (b.w < a.w) ? b.w : a.w;
+    float w = __fsub_rn(xx2, xx1); w = (0.0f < w) ? w : 0.0f;
+    float h = __fsub_rn(yy2, yy1); h = (0.0f < h) ? h : 0.0f;
+    const float inter = __fmul_rn(w, h);
+    const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+    return ovr >= thr_up;  // == ((double)ovr > iou_threshold); NaN -> false -> kept
+}
+
+// ------------------------------------------------------------------------------------
+// mask: persistent loop over upper-triangular 64x64 tiles of all segments
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
+                                                 float thr_up, unsigned long long* __restrict__ mask) {
+    __shared__ float4 cbox[64];
+    __shared__ float carea[64];
+    __shared__ int sh_g, sh_r, sh_c;
+    const int tid = threadIdx.x;
+    if (s.totals[2] != 0) return;  // mask workspace too small: host retries with totals[1] words
+    const long long total = s.totals[0];
+    for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+        if (tid == 0) {
+            int lo = 0, hi = G;  // largest g with tile_pre[g] <= t
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s.tile_pre[mid] <= t) lo = mid; else hi = mid;
+            }
+            const long long tl = t - s.tile_pre[lo];
+            const long long T = s.seg_words[lo];
+            const double d = (double)(2 * T + 1);
+            long long r = (long long)((d - sqrt(d * d - 8.0 * (double)tl)) * 0.5);
+            if (r < 0) r = 0;
+            if (r > T - 1) r = T - 1;
+            while (r + 1 <= T - 1 && (r + 1) * T - (r + 1) * r / 2 <= tl) ++r;
+            while (r > 0 && r * T - r * (r - 1) / 2 > tl) --r;
+            sh_g = lo; sh_r = (int)r; sh_c = (int)(r + (tl - (r * T - r * (r - 1) / 2)));
+        }
+        __syncthreads();
+        const int g = sh_g, r = sh_r, c = sh_c;
+        const int n = s.seg_count[g], T = s.seg_words[g], st = s.seg_start[g];
+        const int ncol = min(64, n - c * 64);
+        if (tid < ncol) {
+            const float4 b = sbox[st + c * 64 + tid];
+            cbox[tid] = b;
+            carea[tid] = box_area_rn(b);
+        }
+        __syncthreads();
+        const int row = r * 64 + tid;
+        if (row < n) {
+            const float4 a = sbox[st + row];
+            const float area_a = box_area_rn(a);
+            unsigned long long word = 0;
+            const int j0 = (r == c) ? tid + 1 : 0;
+            for (int j = j0; j < ncol; ++j)
+                if (iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1ull << j;
+            mask[s.mask_off[g] + (long long)row * T + c] = word;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// sweep: one CTA per segment. keepbits word b of segment g holds the kept flags of its
+// boxes 64b..64b+63 (sorted order). max_keep > 0 stops once that many boxes are kept
+// (later boxes of the segment all score lower, so they cannot enter a global top-max_keep).
+// ------------------------------------------------------------------------------------
+constexpr int kSweepThreads = 256;
+
+__global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                            unsigned long long* __restrict__ keepbits, int max_keep) {
+    extern __shared__ unsigned long long removed[];
+    __shared__ unsigned long long diag[64];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int n = s.seg_count[g];
+    const int T = s.seg_words[g];
+    const bool overflow = s.totals[2] != 0;
+    if (n == 0 || overflow) { if (tid == 0) s.seg_kept[g] = 0; return; }
+    const unsigned long long* m = mask + s.mask_off[g];
+    unsigned long long* kb = keepbits + s.keep_off[g];
+    for (int w = tid; w < T; w += kSweepThreads) removed[w] = 0;
+    int kept = 0;
+    for (int b = 0; b < T; ++b) {
+        const int nb = min(64, n - b * 64);
+        if (tid < nb) diag[tid] = m[(long long)(b * 64 + tid) * T + b];
+        __syncthreads();
+        unsigned long long cur = removed[b];
+        unsigned long long keepw = 0;
+        if (nb == 64) {
+#pragma unroll 16
+            for (int t = 0; t < 64; ++t) {
+                const bool k = !((cur >> t) & 1ull);
+                keepw |= k ? (1ull << t) : 0ull;
+                cur |= k ? diag[t] : 0ull;
+            }
+        } else {
+            for (int t = 0; t < nb; ++t) {
+                const bool k = !((cur >> t) & 1ull);
+                keepw |= k ? (1ull << t) : 0ull;
+                cur |= k ? diag[t] : 0ull;
+            }
+        }
+        if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
+            // trim to exactly max_keep kept boxes in this segment
+            int extra = kept + __popcll(keepw) - max_keep;
+            while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+        }
+        kept += __popcll(keepw);
+        if (tid == 0) kb[b] = keepw;
+        const bool done = (max_keep > 0 && kept >= max_keep);
+        if (done) {
+            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
+            break;
+        }
+        for (int w = b + 1 + tid; w < T; w += kSweepThreads) {
+            unsigned long long acc = 0, bits = keepw;
+            while (bits) {
+                const int t0 = __ffsll((long long)bits) - 1; bits &= bits - 1;
+                unsigned long long v0 = m[(long long)(b * 64 + t0) * T + w], v1 = 0, v2 = 0, v3 = 0;
+                if (bits) { const int t1 = __ffsll((long long)bits) - 1; bits &= bits - 1; v1 = m[(long long)(b * 64 + t1) * T + w]; }
+                if (bits) { const int t2 = __ffsll((long long)bits) - 1; bits &= bits - 1; v2 = m[(long long)(b * 64 + t2) * T + w]; }
+                if (bits) { const int t3 = __ffsll((long long)bits) - 1; bits &= bits - 1; v3 = m[(long long)(b * 64 + t3) * T + w]; }
+                acc |= (v0 | v1) | (v2 | v3);
+            }
+            removed[w] |= acc;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s.seg_kept[g] = kept;
+}
+
+inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsigned long long); }
+
+// Host helper: launch meta + mask + sweep on prepared sorted boxes.
+inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max_seg_elems, double iou_threshold,
+                                 unsigned long long* mask, unsigned long long* keepbits, int max_keep,
+                                 cudaStream_t stream) {
+    const float thr_up = strict_gt_threshold(iou_threshold);
+    k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask);
+    MB_LAUNCH_CHECK();
+    const int smem = sweep_smem_bytes(ceil_div(max_seg_elems, 64) + 1);
+    if (smem > 48 * 1024) {
+        if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
+        MB_CUDA(cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    k_nms_sweep<<<G, kSweepThreads, smem, stream>>>(s, mask, keepbits, max_keep);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+}  // namespace mb

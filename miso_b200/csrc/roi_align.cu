@@ -1,0 +1,348 @@
+// roi_align.cu — MultiScaleRoIAlign / roi_align forward for NCHW fp32 features.
+//
+// Replaces tv:ops/poolers.py:147-227 (per-level where/gather/roi_align/scatter loop) and
+// torchvision::roi_align (tv:ops/roi_align.py:203-260 -> tv-csrc:ops/cuda/roi_align_kernel.cu:470)
+// with ONE launch over all levels. Arithmetic follows the CPU kernel
+// (tv-csrc:ops/cpu/roi_align_kernel.cpp:393): sample coordinates are
+// computed with one fp32 rounding per operation, and in `exact` mode the bilinear sum keeps the
+// reference's operation order so results are bit-identical; otherwise FMAs are used (<=1e-5 rel).
+//
+// Staged kernel (sampling_ratio > 0, the detection models' configuration):
+//   CTA = (RoI, 32-channel chunk). The RoI's bilinear footprint (all rows/columns its samples
+//   touch) is copied once from the NCHW planes into shared memory as [channel][row][col] with a
+//   plane pitch == 1 (mod 32) words, so that "lane = channel" reads of one tap hit 32 distinct
+//   banks. Tap indices and weights are warp-uniform and computed once per RoI. Outputs are
+//   collected in shared memory and written as one contiguous, 16-byte-vectorised block of
+//   32*PH*PW floats (the [K,C,PH,PW] layout makes a channel chunk of one RoI contiguous).
+//   Footprints larger than the staging buffer are processed in groups of output rows; a
+//   footprint whose single output row does not fit falls back to direct global gathers.
+// Direct kernel (sampling_ratio <= 0 or very large bins): one thread per output element.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace mb {
+
+constexpr int kRoiThreads = 256;
+constexpr int kRoiWarps = kRoiThreads / 32;
+constexpr int kChunk = 32;       // channels per CTA
+constexpr int kMaxSamples = 64;  // sampling_ratio * pooled size per axis, staged kernel
+
+struct Tap {       // one sample along one axis
+    int lo, hi;    // pixel indices
+    float l, h;    // weights of hi / lo pixel (ly, hy in the reference)
+    int valid;
+};
+
+struct RoiGeom {
+    int level, batch;
+    int H, W;
+    float start_h, start_w, bin_h, bin_w;
+    int grid_h, grid_w;
+    float count;
+};
+
+__device__ __forceinline__ int roi_level(const float* r, const mb_roi_align_params& p) {
+    // LevelMapper (tv:ops/poolers.py:73-84) as monotone thresholds on the fp32 box area
+    const float area = __fmul_rn(__fsub_rn(r[3], r[1]), __fsub_rn(r[4], r[2]));
+    int lvl = 0;
+    for (int i = 0; i + 1 < p.num_levels; ++i) lvl += (area >= p.level_thresholds[i]) ? 1 : 0;
+    return lvl;
+}
+
+__device__ __forceinline__ void roi_geometry(const float* r, const mb_roi_align_params& p, RoiGeom& g) {
+    g.level = roi_level(r, p);
+    g.batch = (int)r[0];
+    g.H = p.height[g.level];
+    g.W = p.width[g.level];
+    const float scale = p.spatial_scale[g.level];
+    const float off = p.aligned ? 0.5f : 0.0f;
+    const float sw = __fsub_rn(__fmul_rn(r[1], scale), off);
+    const float sh = __fsub_rn(__fmul_rn(r[2], scale), off);
+    const float ew = __fsub_rn(__fmul_rn(r[3], scale), off);
+    const float eh = __fsub_rn(__fmul_rn(r[4], scale), off);
+    float rw = __fsub_rn(ew, sw), rh = __fsub_rn(eh, sh);
+    if (!p.aligned) { rw = fmaxf(rw, 1.0f); rh = fmaxf(rh, 1.0f); }
+    g.start_h = sh; g.start_w = sw;
+    g.bin_h = __fdiv_rn(rh, (float)p.pooled_h);
+    g.bin_w = __fdiv_rn(rw, (float)p.pooled_w);
+    g.grid_h = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rh, (float)p.pooled_h));
+    g.grid_w = p.sampling_ratio > 0 ? p.sampling_ratio : (int)ceilf(__fdiv_rn(rw, (float)p.pooled_w));
+    g.count = (float)max(g.grid_h * g.grid_w, 1);
+}
+
+// one axis of bilinear_interpolate / pre_calc_for_bilinear_interpolate
+__device__ __forceinline__ Tap make_tap(float start, float bin, int p_idx, int i_idx, int grid, int size) {
+    Tap t;
+    float v = __fadd_rn(__fadd_rn(start, __fmul_rn((float)p_idx, bin)),
+                        __fdiv_rn(__fmul_rn(__fadd_rn((float)i_idx, 0.5f), bin), (float)grid));
+    t.valid = !(v < -1.0f || v > (float)size);
+    if (v <= 0.0f) v = 0.0f;
+    int lo = (int)v, hi;
+    if (lo >= size - 1) { hi = lo = size - 1; v = (float)lo; } else hi = lo + 1;
+    t.lo = lo; t.hi = hi;
+    t.l = __fsub_rn(v, (float)lo);
+    t.h = __fsub_rn(1.0f, t.l);
+    if (!t.valid) { t.lo = 0; t.hi = 0; t.l = 0.f; t.h = 0.f; }
+    return t;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float bilinear4(float hy, float ly, float hx, float lx, float v1, float v2,
+                                           float v3, float v4, float acc) {
+    if (EXACT) {
+        const float w1 = __fmul_rn(hy, hx), w2 = __fmul_rn(hy, lx), w3 = __fmul_rn(ly, hx), w4 = __fmul_rn(ly, lx);
+        float t = __fmul_rn(w1, v1);
+        t = __fadd_rn(t, __fmul_rn(w2, v2));
+        t = __fadd_rn(t, __fmul_rn(w3, v3));
+        t = __fadd_rn(t, __fmul_rn(w4, v4));
+        return __fadd_rn(acc, t);
+    } else {
+        const float top = fmaf(lx, v2, hx * v1);
+        const float bot = fmaf(lx, v4, hx * v3);
+        return fmaf(hy, top, fmaf(ly, bot, acc));
+    }
+}
+
+template <bool EXACT, bool SR2>
+__global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_align_params p,
+                                                                 const float* __restrict__ rois, int num_rois,
+                                                                 float* __restrict__ out, int* __restrict__ levels_out,
+                                                                 int stage_floats) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ Tap ytab[kMaxSamples], xtab[kMaxSamples];
+    __shared__ RoiGeom geom;
+    // sampling_ratio == 2: per output row / column, both samples packed for 128-bit broadcast loads
+    __shared__ __align__(16) int4 yoff2[kMaxSamples / 2], xoff2[kMaxSamples / 2];
+    __shared__ __align__(16) float4 ywt2[kMaxSamples / 2], xwt2[kMaxSamples / 2];
+
+    const int chunks = (p.channels + kChunk - 1) / kChunk;
+    const int k = blockIdx.x / chunks;
+    const int c0 = (blockIdx.x % chunks) * kChunk;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
+    const int opitch = (nbins & 1) ? nbins : nbins + 1;  // odd pitch: lane=channel stores hit 32 banks
+    float* out_s = smem;                       // [kChunk][opitch]
+    float* patch = smem + kChunk * opitch;     // [kChunk][pitch]
+    const int patch_floats = stage_floats - kChunk * opitch;
+
+    const float* r = rois + (size_t)k * 5;
+    if (tid == 0) {
+        RoiGeom g;
+        roi_geometry(r, p, g);
+        geom = g;
+        if (levels_out != nullptr && c0 == 0) levels_out[k] = g.level;
+    }
+    __syncthreads();
+    const RoiGeom g = geom;
+    const int ny = PH * g.grid_h, nx = PW * g.grid_w;
+    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid / g.grid_h, tid % g.grid_h, g.grid_h, g.H);
+    if (tid >= 64 && tid < 64 + nx) {
+        const int i = tid - 64;
+        xtab[i] = make_tap(g.start_w, g.bin_w, i / g.grid_w, i % g.grid_w, g.grid_w, g.W);
+    }
+    __syncthreads();
+
+    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
+    // footprint columns (all valid x samples)
+    int x0 = 0x7fffffff, x1 = -1;
+    for (int i = 0; i < nx; ++i)
+        if (xtab[i].valid) { x0 = min(x0, xtab[i].lo); x1 = max(x1, xtab[i].hi); }
+    const int cols = x1 - x0 + 1;
+    const int c = c0 + lane;
+    const bool c_ok = c < p.channels;
+    const float* feat = p.features[g.level];
+    const size_t plane = (size_t)g.H * g.W;
+    const float* base = feat + ((size_t)(bad_batch ? 0 : g.batch) * p.channels + c0) * plane;
+
+    int ph0 = 0;
+    while (ph0 < PH) {
+        // ---- choose the largest group of output rows [ph0, ph1) whose footprint fits ----
+        int gy0 = 0x7fffffff, gy1 = -1, ph1 = ph0;
+        bool direct = false;
+        if (x1 < 0 || bad_batch) {
+            ph1 = PH;  // nothing to sample: zeros
+        } else {
+            while (ph1 < PH) {
+                int ny0 = gy0, ny1 = gy1;
+                for (int i = ph1 * g.grid_h; i < (ph1 + 1) * g.grid_h; ++i)
+                    if (ytab[i].valid) { ny0 = min(ny0, ytab[i].lo); ny1 = max(ny1, ytab[i].hi); }
+                const int rows_n = ny1 >= 0 ? ny1 - ny0 + 1 : 0;
+                const int pix = rows_n * cols;
+                const int pitch_n = pix + ((33 - (pix & 31)) & 31);
+                if (pitch_n * kChunk > patch_floats) break;
+                gy0 = ny0; gy1 = ny1; ++ph1;
+            }
+            if (ph1 == ph0) { direct = true; ph1 = ph0 + 1; }
+        }
+        const int rows = gy1 >= 0 ? gy1 - gy0 + 1 : 0;
+        const int pix = rows * cols;
+        const int pitch = pix + ((33 - (pix & 31)) & 31);
+
+        // ---- stage the footprint: warp per (channel,row), lanes along x (coalesced) ----
+        if (!direct && rows > 0) {
+            const int nch = min(kChunk, p.channels - c0);
+            for (int cr = warp; cr < nch * rows; cr += kRoiWarps) {
+                const int cc = cr / rows, rr = cr - cc * rows;
+                const float* src = base + (size_t)cc * plane + (size_t)(gy0 + rr) * g.W + x0;
+                float* dst = patch + cc * pitch + rr * cols;
+                for (int x = lane; x < cols; x += 32) dst[x] = __ldg(src + x);
+            }
+        }
+        if (SR2 && !direct && rows > 0) {
+            if (tid < ph1 - ph0) {
+                const Tap a = ytab[(ph0 + tid) * 2], b = ytab[(ph0 + tid) * 2 + 1];
+                const int alo = a.valid ? a.lo : gy0, ahi = a.valid ? a.hi : gy0;
+                const int blo = b.valid ? b.lo : gy0, bhi = b.valid ? b.hi : gy0;
+                yoff2[tid] = make_int4((alo - gy0) * cols - x0, (ahi - gy0) * cols - x0,
+                                       (blo - gy0) * cols - x0, (bhi - gy0) * cols - x0);
+                ywt2[tid] = make_float4(a.h, a.l, b.h, b.l);
+            }
+            if (tid >= 32 && tid < 32 + PW) {
+                const int i = tid - 32;
+                const Tap a = xtab[i * 2], b = xtab[i * 2 + 1];
+                xoff2[i] = make_int4(a.valid ? a.lo : x0, a.valid ? a.hi : x0, b.valid ? b.lo : x0, b.valid ? b.hi : x0);
+                xwt2[i] = make_float4(a.h, a.l, b.h, b.l);
+            }
+        }
+        __syncthreads();
+
+        // ---- bins of this group: warp per bin, lane per channel ----
+        const int gbins = (ph1 - ph0) * PW;
+        const float* sp = patch + lane * pitch;
+        const float* gp = base + (size_t)lane * plane;
+        for (int b = warp; b < gbins; b += kRoiWarps) {
+            const int ph = ph0 + b / PW, pw = b - (b / PW) * PW;
+            float acc = 0.0f;
+            if (SR2 && !direct) {
+                if (c_ok && rows > 0) {
+                    const int4 yo = yoff2[ph - ph0], xo = xoff2[pw];
+                    const float4 yw = ywt2[ph - ph0], xw = xwt2[pw];
+                    // sample (iy=0, ix=0), (0,1), (1,0), (1,1) in the reference's loop order
+                    acc = bilinear4<EXACT>(yw.x, yw.y, xw.x, xw.y, sp[yo.x + xo.x], sp[yo.x + xo.y], sp[yo.y + xo.x], sp[yo.y + xo.y], acc);
+                    acc = bilinear4<EXACT>(yw.x, yw.y, xw.z, xw.w, sp[yo.x + xo.z], sp[yo.x + xo.w], sp[yo.y + xo.z], sp[yo.y + xo.w], acc);
+                    acc = bilinear4<EXACT>(yw.z, yw.w, xw.x, xw.y, sp[yo.z + xo.x], sp[yo.z + xo.y], sp[yo.w + xo.x], sp[yo.w + xo.y], acc);
+                    acc = bilinear4<EXACT>(yw.z, yw.w, xw.z, xw.w, sp[yo.z + xo.z], sp[yo.z + xo.w], sp[yo.w + xo.z], sp[yo.w + xo.w], acc);
+                }
+            } else if (c_ok && (direct || rows > 0)) {
+                for (int iy = 0; iy < g.grid_h; ++iy) {
+                    const Tap Y = ytab[ph * g.grid_h + iy];
+                    if (!Y.valid) continue;
+                    for (int ix = 0; ix < g.grid_w; ++ix) {
+                        const Tap X = xtab[pw * g.grid_w + ix];
+                        if (!X.valid) continue;
+                        float v1, v2, v3, v4;
+                        if (!direct) {
+                            const int rlo = (Y.lo - gy0) * cols - x0, rhi = (Y.hi - gy0) * cols - x0;
+                            v1 = sp[rlo + X.lo]; v2 = sp[rlo + X.hi]; v3 = sp[rhi + X.lo]; v4 = sp[rhi + X.hi];
+                        } else {
+                            v1 = __ldg(gp + Y.lo * g.W + X.lo); v2 = __ldg(gp + Y.lo * g.W + X.hi);
+                            v3 = __ldg(gp + Y.hi * g.W + X.lo); v4 = __ldg(gp + Y.hi * g.W + X.hi);
+                        }
+                        acc = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1, v2, v3, v4, acc);
+                    }
+                }
+            }
+            out_s[lane * opitch + ph * PW + pw] = __fdiv_rn(acc, g.count);
+        }
+        __syncthreads();
+        ph0 = ph1;
+    }
+
+    // ---- one contiguous block of min(32, C-c0)*nbins floats per (RoI, chunk) ----
+    const int nch = min(kChunk, p.channels - c0);
+    const int total = nch * nbins;
+    float* dst = out + ((size_t)k * p.channels + c0) * nbins;
+    if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(out_s);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = tid; i < total / 4; i += kRoiThreads) d4[i] = s4[i];
+    } else {
+        for (int ch = warp; ch < nch; ch += kRoiWarps)
+            for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = out_s[ch * opitch + b];
+    }
+}
+
+// Direct kernel: any sampling_ratio (incl. adaptive), any pooled size. One thread per output.
+__global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_params p, const float* __restrict__ rois,
+                                                         long long total, float* __restrict__ out,
+                                                         int* __restrict__ levels_out) {
+    const int PH = p.pooled_h, PW = p.pooled_w;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int pw = (int)(idx % PW);
+        const int ph = (int)((idx / PW) % PH);
+        const int c = (int)((idx / ((long long)PW * PH)) % p.channels);
+        const long long k = idx / ((long long)PW * PH * p.channels);
+        const float* r = rois + k * 5;
+        RoiGeom g;
+        roi_geometry(r, p, g);
+        if (levels_out != nullptr && c == 0 && ph == 0 && pw == 0) levels_out[k] = g.level;
+        float acc = 0.0f;
+        if (g.batch >= 0 && g.batch < p.num_images) {
+            const float* plane = p.features[g.level] + ((size_t)g.batch * p.channels + c) * (size_t)g.H * g.W;
+            for (int iy = 0; iy < g.grid_h; ++iy) {
+                const Tap Y = make_tap(g.start_h, g.bin_h, ph, iy, g.grid_h, g.H);
+                if (!Y.valid) continue;
+                for (int ix = 0; ix < g.grid_w; ++ix) {
+                    const Tap X = make_tap(g.start_w, g.bin_w, pw, ix, g.grid_w, g.W);
+                    if (!X.valid) continue;
+                    acc = bilinear4<true>(Y.h, Y.l, X.h, X.l, __ldg(plane + Y.lo * g.W + X.lo),
+                                          __ldg(plane + Y.lo * g.W + X.hi), __ldg(plane + Y.hi * g.W + X.lo),
+                                          __ldg(plane + Y.hi * g.W + X.hi), acc);
+                }
+            }
+        }
+        out[idx] = __fdiv_rn(acc, g.count);
+    }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" size_t mb_roi_align_workspace_bytes(int64_t) { return 256; }
+
+extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const float* rois, int64_t num_rois,
+                                       float* out, int32_t* levels_out, void* /*workspace*/,
+                                       size_t /*workspace_bytes*/, mb_stream_t stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!pp) return MB_ERR_INVALID_ARG;
+    const mb_roi_align_params p = *pp;
+    if (p.num_levels < 1 || p.num_levels > MB_MAX_LEVELS || p.channels < 1 || p.pooled_h < 1 || p.pooled_w < 1 ||
+        p.num_images < 1 || num_rois < 0)
+        return MB_ERR_INVALID_ARG;
+    for (int l = 0; l < p.num_levels; ++l)
+        if (!p.features[l] || p.height[l] < 1 || p.width[l] < 1) return MB_ERR_INVALID_ARG;
+    if (num_rois == 0) return MB_OK;
+    if (!rois || !out) return MB_ERR_INVALID_ARG;
+    const int nbins = p.pooled_h * p.pooled_w;
+    const long long chunks = (p.channels + kChunk - 1) / kChunk;
+    const bool staged = p.sampling_ratio > 0 && p.sampling_ratio * p.pooled_h <= kMaxSamples &&
+                        p.sampling_ratio * p.pooled_w <= kMaxSamples && nbins <= 512 &&
+                        num_rois * chunks < (1ll << 31);
+    if (staged) {
+        // staging buffer: outputs + a footprint of up to ~320 pixels per channel (4 CTAs/SM at 7x7)
+        const int opitch = (nbins & 1) ? nbins : nbins + 1;
+        const int stage_floats = kChunk * opitch + kChunk * 353;
+        const int smem = stage_floats * (int)sizeof(float);
+        if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
+        const int grid = (int)(num_rois * chunks);
+#define MB_ROI_LAUNCH(E, S)                                                                                  \
+    do {                                                                                                    \
+        MB_CUDA(cudaFuncSetAttribute(k_roi_align_staged<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        k_roi_align_staged<E, S><<<grid, kRoiThreads, smem, stream>>>(p, rois, (int)num_rois, out, levels_out, stage_floats); \
+    } while (0)
+        const bool sr2 = p.sampling_ratio == 2;
+        if (p.exact) { if (sr2) MB_ROI_LAUNCH(true, true); else MB_ROI_LAUNCH(true, false); }
+        else { if (sr2) MB_ROI_LAUNCH(false, true); else MB_ROI_LAUNCH(false, false); }
+#undef MB_ROI_LAUNCH
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
+    const long long total = num_rois * (long long)p.channels * nbins;
+    const int grid = (int)min((long long)kNumSMs * 32, ceil_div64(total, 256));
+    k_roi_align_direct<<<grid, 256, 0, stream>>>(p, rois, total, out, levels_out);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}

@@ -1,0 +1,187 @@
+"""GPU parity tests of the torchvision-signature operators (through the C ABI) against the CPU
+oracle and the committed golden vectors. Bit-exact for indices; RoIAlign exact mode bit-exact,
+fast mode within 1e-5; decoded boxes within 1e-5 of each box's scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import detection as D
+from oracle import native
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from miso_b200 import ops as o
+    o._lib.load()
+    return o
+
+
+def test_nms_cases_bit_exact(ops, golden_dir):
+    g = load(golden_dir, "nms")
+    for name, b, s, thr in cases.nms_cases():
+        keep = ops.nms(cu(b), cu(s), thr).cpu().numpy()
+        assert keep.dtype == np.int64
+        assert np.array_equal(keep, g[name + "/keep"]), name
+        assert np.array_equal(keep, native.nms(b, s, thr)), name
+
+
+def test_nms_empty_and_shapes(ops):
+    e = ops.nms(torch.zeros((0, 4), device=DEV), torch.zeros((0,), device=DEV), 0.5)
+    assert e.shape == (0,) and e.dtype == torch.int64 and e.device.type == "cuda"
+    with pytest.raises(Exception):
+        ops.nms(torch.zeros((3, 5), device=DEV), torch.zeros((3,), device=DEV), 0.5)
+
+
+def test_batched_nms_both_strategies_bit_exact(ops, golden_dir):
+    g = load(golden_dir, "batched_nms")
+    for name, b, s, idx, thr in cases.batched_nms_cases():
+        v = ops.batched_nms(cu(b), cu(s), cu(idx), thr, strategy="vanilla").cpu().numpy()
+        t = ops.batched_nms(cu(b), cu(s), cu(idx), thr, strategy="trick").cpu().numpy()
+        assert np.array_equal(v, g[name + "/vanilla"]), name
+        assert np.array_equal(t, g[name + "/trick"]), name
+    # auto follows torchvision's CUDA rule (trick below 100k elements)
+    name, b, s, idx, thr = cases.batched_nms_cases()[1]
+    assert np.array_equal(ops.batched_nms(cu(b), cu(s), cu(idx), thr).cpu().numpy(), g[name + "/trick"])
+    e = ops.batched_nms(torch.zeros((0, 4), device=DEV), torch.zeros((0,), device=DEV),
+                        torch.zeros((0,), dtype=torch.int64, device=DEV), 0.5)
+    assert e.numel() == 0
+
+
+def test_batched_nms_arbitrary_category_values(ops):
+    rng = np.random.default_rng(8)
+    b, s = cases.random_boxes(rng, 700, extent=150.0), cases.distinct_scores(rng, 700)
+    idx = rng.choice(np.array([-7, 3, 10**9, 123456789012], dtype=np.int64), 700)
+    v = ops.batched_nms(cu(b), cu(s), cu(idx), 0.5, strategy="vanilla").cpu().numpy()
+    assert np.array_equal(v, D.batched_nms_vanilla(b, s, idx, 0.5))
+
+
+def test_nms_medium_stress(ops):
+    """20k boxes, single class, tie-heavy scores; 30k boxes over 80 classes (scaled-down cfg 4)."""
+    rng = np.random.default_rng(2024)
+    n = 20000
+    c = rng.uniform(0, 2048, (n, 2)); wh = np.exp(rng.uniform(np.log(8), np.log(256), (n, 2)))
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    s = (np.floor(rng.uniform(0, 1, n) * 4096) / 4096).astype(np.float32)
+    assert np.array_equal(ops.nms(cu(b), cu(s), 0.5).cpu().numpy(), native.nms(b, s, 0.5))
+    n = 30000
+    c = rng.uniform(0, 2048, (n, 2)); wh = np.exp(rng.uniform(np.log(8), np.log(256), (n, 2)))
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+    s = cases.distinct_scores(rng, n)
+    idx = rng.integers(0, 80, n).astype(np.int64)
+    for thr in (0.3, 0.7):
+        v = ops.batched_nms(cu(b), cu(s), cu(idx), thr, strategy="vanilla").cpu().numpy()
+        assert np.array_equal(v, D.batched_nms_vanilla(b, s, idx, thr))
+
+
+def test_roi_align_exact_matches_golden_and_oracle(ops, golden_dir):
+    g = load(golden_dir, "roi_align")
+    for name, x, rois, scale, P, sr, aligned in cases.roi_align_cases():
+        out = ops.roi_align(cu(x), cu(rois), P, scale, sr, aligned, exact=True).cpu().numpy()
+        assert out.shape == (rois.shape[0], x.shape[1], P, P)
+        assert np.array_equal(out[:, cases.ROI_GOLDEN_CHANNELS], g[name]), name
+        assert np.array_equal(out, native.roi_align(x, rois, scale, P, P, sr, aligned)), name
+
+
+def test_roi_align_fast_mode_within_tolerance(ops):
+    for name, x, rois, scale, P, sr, aligned in cases.roi_align_cases():
+        if sr != 2:
+            continue
+        out = ops.roi_align(cu(x), cu(rois), P, scale, sr, aligned, exact=False).cpu().numpy()
+        ref = native.roi_align(x, rois, scale, P, P, sr, aligned)
+        tol = 1e-5 * np.abs(ref) + 1e-5 * np.abs(x).max()   # rtol 1e-5, atol 1e-5 of the feature scale
+        assert np.all(np.abs(out - ref) <= tol), name
+
+
+def test_roi_align_list_input_and_errors(ops):
+    x = torch.randn(2, 8, 20, 20, device=DEV)
+    b0 = torch.tensor([[1.0, 2.0, 10.0, 12.0]], device=DEV)
+    b1 = torch.tensor([[0.0, 0.0, 5.0, 5.0], [3.0, 3.0, 19.0, 18.0]], device=DEV)
+    out = ops.roi_align(x, [b0, b1], (7, 5), 0.5, 2)
+    rois = np.array([[0, 1, 2, 10, 12], [1, 0, 0, 5, 5], [1, 3, 3, 19, 18]], np.float32)
+    assert np.array_equal(out.cpu().numpy(), native.roi_align(x.cpu().numpy(), rois, 0.5, 7, 5, 2, False))
+    with pytest.raises(Exception):
+        ops.roi_align(x, torch.zeros((3, 4), device=DEV), 7)
+    assert ops.roi_align(x, torch.zeros((0, 5), device=DEV), 7).shape == (0, 8, 7, 7)
+
+
+@pytest.mark.parametrize("tag,P", [("box7", 7), ("mask14", 14)])
+def test_multiscale_roi_align_single_launch(ops, golden_dir, tag, P):
+    g = load(golden_dir, "multiscale_" + tag)
+    feats, boxes, shapes = cases.multiscale_case()
+    pool = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], P, 2)
+    x = {str(i): cu(f) for i, f in enumerate(feats)}
+    x["pool"] = torch.zeros(1, device=DEV)   # ignored like in the reference (not in featmap_names)
+    out, levels = pool(x, [cu(b) for b in boxes], shapes, return_levels=True)
+    assert np.array_equal(levels.cpu().numpy().astype(np.int64), g["levels"])
+    assert pool.scales == list(g["scales"])
+    out = out.cpu().numpy()
+    assert np.array_equal(out[:, ::4], g["out"])
+    assert np.array_equal(out, D.multiscale_roi_align(feats, boxes, shapes, P, 2))
+
+
+def test_roi_align_full_size_properties(ops):
+    """BASELINE config 2 shapes (4 x 256 ch pyramid of an 800^2 image, 1000 RoIs/img): properties
+    that need no oracle run — linearity in the features and agreement of exact/fast modes — plus
+    a bit-exact oracle check on a random subset of RoIs."""
+    rng = np.random.default_rng(0)
+    n, c = 4, 256
+    feats = [torch.randn(n, c, 800 // s, 800 // s, device=DEV) for s in (4, 8, 16, 32)]
+    boxes = [cu(cases.stress_rois(rng, 1000, (800, 800))) for _ in range(n)]
+    shapes = [(800, 800)] * n
+    pool = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    x = {str(i): f for i, f in enumerate(feats)}
+    out, levels = pool(x, boxes, shapes, return_levels=True)
+    assert out.shape == (4000, 256, 7, 7)
+    assert set(levels.cpu().tolist()) == {0, 1, 2, 3}
+    x2 = {k: 2.0 * v for k, v in x.items()}
+    assert torch.equal(pool(x2, boxes, shapes), 2.0 * out)          # exact in fp32: scaling by 2
+    fast = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, exact=False)(x, boxes, shapes)
+    assert torch.allclose(fast, out, rtol=1e-5, atol=5e-5)
+    pick = np.sort(rng.choice(4000, 64, replace=False))
+    sub_boxes = [boxes[i].cpu().numpy()[pick[pick // 1000 == i] % 1000] for i in range(n)]
+    ref = D.multiscale_roi_align([f.cpu().numpy() for f in feats], sub_boxes, shapes, 7, 2)
+    assert np.array_equal(out[torch.from_numpy(pick).to(DEV)].cpu().numpy(), ref)
+
+
+def test_box_ops(ops, golden_dir):
+    g = load(golden_dir, "boxes")
+    b, rel, wild = g["boxes"], g["rel"], g["wild"]
+    d1 = ops.decode_boxes(cu(rel[:, :4].copy()), [cu(b)], (1.0, 1.0, 1.0, 1.0)).cpu().numpy()
+    d2 = ops.decode_boxes(cu(rel), [cu(b[:1200]), cu(b[1200:])], (10.0, 10.0, 5.0, 5.0)).cpu().numpy()
+    assert d1.shape == (2000, 1, 4) and d2.shape == (2000, 3, 4)
+    assert cases.box_rel_err(d1, g["decode_rpn"]) < 1e-5
+    assert cases.box_rel_err(d2, g["decode_roi"]) < 1e-5
+    clip = ops.clip_boxes_to_image(cu(wild), (480, 640))
+    assert np.array_equal(clip.cpu().numpy(), g["clip"])
+    assert np.array_equal(ops.remove_small_boxes(clip, 1e-3).cpu().numpy(), g["small_1e-3"])
+    assert np.array_equal(ops.remove_small_boxes(clip, 20.0).cpu().numpy(), g["small_20"])
+    for a in ("xyxy", "xywh", "cxcywh"):
+        for c in ("xyxy", "xywh", "cxcywh"):
+            assert np.array_equal(ops.box_convert(cu(b), a, c).cpu().numpy(), g[f"convert_{a}_{c}"]), (a, c)
+    with pytest.raises(ValueError):
+        ops.box_convert(cu(b), "xyxy", "bogus")
+    assert np.array_equal(ops.resize_boxes(cu(b), [800, 800], [1024, 1024]).cpu().numpy(), g["resize"])
+    assert np.array_equal(ops.resize_boxes(cu(b), [800, 1216], [683, 1024]).cpu().numpy(), g["resize2"])
+
+
+def test_grid_anchors(ops, golden_dir):
+    g = load(golden_dir, "anchors")
+    outs = []
+    for lvl, (gh, gw) in enumerate(g["grids"]):
+        base = ops.base_anchors(cases.RPN_SIZES[lvl], cases.RPN_RATIOS[lvl])
+        outs.append(ops.grid_anchors(base, (gh, gw), (224 // gh, 288 // gw), DEV).cpu().numpy())
+    assert np.array_equal(np.concatenate(outs), g["anchors"])

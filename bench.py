@@ -1,0 +1,397 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the detection post-processing + RoIAlign hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm, one process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...   (reference CPU arm, rank 0 only)
+
+A "step" is one pass of the hot path over one batch of synthetic inputs of BASELINE.json's
+config 2 (Faster R-CNN R50-FPN, batch 4, 1024^2 images resized to 800^2, 1000 RPN proposals per
+image, 256-channel pyramid, 7x7 RoIAlign, 300 detections per image): RPN post-head stage ->
+MultiScaleRoIAlign -> detection post-processing -> score filter + crop extraction. The CNN parts
+(backbone, RPN head, box head) are not on this path; their outputs are seeded random tensors.
+
+  value  detections/s (detections that pass miso's score filter and are cropped), inputs resident
+         in HBM, CUDA-event timed, max over ranks.
+  e2e    the same metric with HOST (pinned) inputs: per step H2D of every input, the hot path,
+         D2H of the detections and crop bytes.
+  roofline  RoIAlign kernel: algorithmic bytes / mean CUDA-event duration of its
+         launches inside the timed region, against the measured HBM peak.
+  cpu_baseline  the CPU oracle port of the same path on one image of the batch (rank 0, N=1).
+With N > 1 every rank runs the same per-GPU batch as a shard of mosaic tiles (weak scaling); the
+step then also contains the path's one exchange: an NCCL all-gather of the per-rank detection
+blocks followed by the cross-tile seam NMS.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "detections_per_sec_posthead_path"
+UNIT = "detections/s"
+
+
+# ----------------------------------------------------------------------------------------------
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--fast-roi-align", action="store_true", help="FMA RoIAlign (<=1e-5) instead of the bit-exact order")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def roi_align_algorithmic_bytes(proposals, counts, shapes, thresholds, scales, channels, pooled, sr=2):
+    """20*K + 4*C*P^2*K + 4*C*sum_levels |union of touched pixels|, the union
+    rasterised exactly from the sample coordinates of the reference formula (Appendix B.2)."""
+    import numpy as np
+    F = np.float32
+    n = proposals.shape[0]
+    maps = [np.zeros((n, gh, gw), dtype=bool) for gh, gw in shapes.feature_grids]
+    k_live = 0
+    for i in range(n):
+        b = proposals[i, :counts[i]]
+        k_live += len(b)
+        area = ((b[:, 2] - b[:, 0]).astype(F) * (b[:, 3] - b[:, 1]).astype(F)).astype(F)
+        lvl = np.zeros(len(b), dtype=np.int64)
+        for t in thresholds:
+            lvl += area >= F(t)
+        for j in range(len(b)):
+            l = lvl[j]
+            gh, gw = shapes.feature_grids[l]
+            sc = F(scales[l])
+            sets = []
+            for lo_c, hi_c, size in ((b[j, 1], b[j, 3], gh), (b[j, 0], b[j, 2], gw)):
+                s0, e0 = F(lo_c * sc), F(hi_c * sc)
+                r = max(F(e0 - s0), F(1.0))
+                binsz = F(r / F(pooled))
+                pp = np.repeat(np.arange(pooled, dtype=F), sr)
+                ii = np.tile(np.arange(sr, dtype=F), pooled)
+                v = ((s0 + (pp * binsz).astype(F)).astype(F) + (((ii + F(0.5)).astype(F) * binsz).astype(F) / F(sr)).astype(F)).astype(F)
+                ok = ~((v < -1.0) | (v > size))
+                v = np.maximum(v[ok], 0)
+                lo = np.minimum(v.astype(np.int64), size - 1)
+                hi = np.minimum(lo + 1, size - 1)
+                sets.append(np.unique(np.concatenate([lo, hi])))
+            if len(sets[0]) and len(sets[1]):
+                maps[l][i][np.ix_(sets[0], sets[1])] = True
+    touched = sum(int(m.sum()) for m in maps)
+    return 20 * k_live + 4 * channels * pooled * pooled * k_live + 4 * channels * touched, k_live, touched
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own CPU implementation of the path: torchvision 0.26 CPU ops and modules
+    (filter_proposals, MultiScaleRoIAlign, postprocess_detections, resize_boxes) plus miso's score
+    filter / coords_int / crop slice (restated: miso.* needs lxml/skimage, absent in this image).
+    Bounded sample: one image of the batch per step. Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import numpy as np
+    import torch
+    from torchvision.models.detection.anchor_utils import AnchorGenerator
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.roi_heads import RoIHeads
+    from torchvision.models.detection.rpn import RegionProposalNetwork, RPNHead, concat_box_prediction_layers
+    from torchvision.models.detection.transform import resize_boxes
+    from torchvision.ops.poolers import MultiScaleRoIAlign
+    from miso_b200 import workload
+    from oracle import miso_path as M
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = workload.faster_rcnn_batch(num_images=1, seed=0, pin=False)
+    h = w.host
+    ag = AnchorGenerator(w.rpn.sizes, w.rpn.aspect_ratios)
+    rpn = RegionProposalNetwork(ag, RPNHead(8, 3), 0.7, 0.3, 256, 0.5, dict(training=2000, testing=w.rpn.pre_nms_top_n),
+                                dict(training=2000, testing=w.rpn.post_nms_top_n), w.rpn.nms_thresh).eval()
+    heads = RoIHeads(None, None, None, 0.5, 0.5, 512, 0.25, (10.0, 10.0, 5.0, 5.0), w.det.score_thresh,
+                     w.det.nms_thresh, w.det.detections_per_img)
+    pool = MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    il = ImageList(torch.zeros(1, 3, *w.shapes.padded_image_size), list(w.shapes.image_sizes))
+    img = h["images"][0].numpy()
+
+    def step():
+        with torch.inference_mode():
+            anchors = ag(il, h["objectness"])
+            napl = [o.shape[1] * o.shape[2] * o.shape[3] for o in h["objectness"]]
+            objectness, deltas = concat_box_prediction_layers(list(h["objectness"]), list(h["deltas"]))
+            proposals = rpn.box_coder.decode(deltas, anchors).view(1, -1, 4)
+            boxes, _ = rpn.filter_proposals(proposals, objectness, il.image_sizes, napl)
+            feats = pool({str(i): f for i, f in enumerate(h["features"])}, boxes, il.image_sizes)
+            k = boxes[0].shape[0]
+            db, ds, dl = heads.postprocess_detections(h["class_logits"][0][:k], h["box_regression"][0][:k], boxes, il.image_sizes)
+            rb = resize_boxes(db[0], list(w.shapes.image_sizes[0]), list(w.shapes.original_image_sizes[0]))
+            _, _, _, _, _, crops = M.filter_and_crop(img, rb.numpy(), ds[0].numpy(), dl[0].numpy(), w.threshold)
+        return len(crops), feats.shape[0]
+
+    for _ in range(min(args.warmup, 2)):
+        step()
+    t0 = time.perf_counter()
+    dets = 0
+    for _ in range(args.steps):
+        d, _ = step()
+        dets += d
+    dt = time.perf_counter() - t0
+    value = dets / dt
+    sample = "1 image of the batch per step (torchvision CPU ops + miso filter/crop restated in numpy)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name.replace(f"batch {w.shapes.num_images}", "batch 4 (sampled: 1 image/step)")},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_baseline_port(w_full, steps=2):
+    """The CPU oracle port of the same path on ONE image of the batch (bounded sample)."""
+    import numpy as np
+    from oracle import native
+    from oracle import pipeline as ref_pipeline
+    from miso_b200 import workload
+    native.lib()
+    w = workload.faster_rcnn_batch(num_images=1, seed=0, pin=False)
+    h = {k: [t.numpy() for t in v] for k, v in w.host.items()}
+    kw = dict(padded_image_size=w.shapes.padded_image_size, image_sizes=w.shapes.image_sizes,
+              original_image_sizes=w.shapes.original_image_sizes, sizes=w.rpn.sizes, aspect_ratios=w.rpn.aspect_ratios,
+              pre_nms_top_n=w.rpn.pre_nms_top_n, post_nms_top_n=w.rpn.post_nms_top_n,
+              detections_per_img=w.det.detections_per_img, threshold=w.threshold)
+    args_ = (h["objectness"], h["deltas"], h["features"], h["class_logits"][0], h["box_regression"][0], h["images"])
+    ref_pipeline.run(*args_, **kw)
+    t0 = time.perf_counter()
+    dets = 0
+    tm = {}
+    for _ in range(steps):
+        out = ref_pipeline.run(*args_, timings=tm, **kw)
+        dets += sum(len(o["crops"]) for o in out)
+    dt = time.perf_counter() - t0
+    return {"value": dets / dt, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"1 image of the batch, {steps} passes of the oracle (C NMS/RoIAlign with OpenMP + numpy); "
+                      f"last pass: rpn {tm.get('rpn_s', 0):.3f}s roi_align {tm.get('roi_align_s', 0):.3f}s "
+                      f"det+crop {tm.get('det_crop_s', 0):.3f}s"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from miso_b200 import mosaic, pipeline, workload
+    from miso_b200 import ops as mops
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = workload.faster_rcnn_batch(num_images=args.batch, seed=rank)
+    hp = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=512 << 20,
+                          exact_roi_align=not args.fast_roi_align, device=dev)
+    d = workload.to_device(w, dev)
+    hp.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
+    n, dpi = args.batch, hp.dpi
+    # mosaic framing for N > 1: this rank's images are tiles at (row=rank, col=i) of a tile grid with 128 px overlap
+    origins = torch.tensor([[rank * 896.0, i * 896.0] for i in range(n)], dtype=torch.float32, device=dev)
+    seam_launches = 0
+
+    def step():
+        hp.step()
+        if world > 1:
+            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
+            gathered = mosaic.exchange(block, world)
+            return mosaic.seam_nms(gathered, w.det.nms_thresh)
+        return None
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    tot = hp.crop_totals.tolist()
+    if tot[2]:
+        raise SystemExit("crop buffer overflow")
+    dets_per_step = tot[0]
+    crop_bytes = tot[1]
+
+    # ---- timed region: K steps, device timed, RoIAlign launches individually bracketed ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    st = hp._stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    roi_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        hp.rpn(st)
+        roi_ev[k][0].record()
+        hp.roi_align(st)
+        roi_ev[k][1].record()
+        hp.detections(st)
+        hp.crops(st)
+        if world > 1:
+            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
+            mosaic.seam_nms(mosaic.exchange(block, world), w.det.nms_thresh)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms, float(dets_per_step)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, total_dets = float(mx[0]), float(sm[1])
+    else:
+        total_dets = float(dets_per_step)
+    ms_per_step = ms / args.steps
+    value = total_dets / (ms_per_step * 1e-3)
+    roi_ms = sorted(a.elapsed_time(b) for a, b in roi_ev)
+    roi_mean_ms = sum(roi_ms) / len(roi_ms)
+
+    # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step ----
+    host_out = {k: torch.empty_like(getattr(hp, k), device="cpu").pin_memory()
+                for k in ("det_boxes", "det_scores", "det_labels", "det_counts", "crop_rects", "crop_xywh", "crop_src",
+                          "crop_offsets", "crop_totals")}
+    host_pix = torch.empty((hp.crop_capacity,), dtype=torch.uint8).pin_memory()
+    dev_lists = {k: d[k] for k in w.host}
+
+    def e2e_step():
+        for k, hs in w.host.items():
+            for src, dst in zip(hs, dev_lists[k]):
+                dst.copy_(src, non_blocking=True)
+        hp.step()
+        for k, ht in host_out.items():
+            ht.copy_(getattr(hp, k), non_blocking=True)
+        torch.cuda.synchronize()
+        nb = int(host_out["crop_totals"][1])
+        host_pix[:nb].copy_(hp.crop_pixels[:nb], non_blocking=True)
+        if world > 1:
+            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
+            b, s, l = mosaic.seam_nms(mosaic.exchange(block, world), w.det.nms_thresh)
+            b.cpu()
+        torch.cuda.synchronize()
+        return nb
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        nb = e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_dets / float(te[0])
+    h2d = w.input_bytes()
+    d2h = sum(t_.numel() * t_.element_size() for t_ in host_out.values()) + crop_bytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (RoIAlign) ----
+    peak, peak_src = peaks()
+    props = hp.proposals.cpu().numpy()
+    cnts = hp.prop_counts.cpu().numpy()
+    q = hp.roi_params
+    thr = [q.level_thresholds[i] for i in range(q.num_levels - 1)]
+    scl = [q.spatial_scale[i] for i in range(q.num_levels)]
+    alg_bytes, k_live, touched = roi_align_algorithmic_bytes(props, cnts, w.shapes, thr, scl, w.shapes.channels, w.shapes.pooled)
+    achieved = alg_bytes / (roi_mean_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_port(w)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": w.name, "per_gpu_batch": args.batch, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
+                   "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
+                   "multi_gpu": "per-rank batch = shard of mosaic tiles; all_gather + seam NMS inside the step" if world > 1 else "single GPU",
+                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
+        "roofline": {"bound": "hbm", "kernel": "k_roi_align_staged", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                     "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
+                     "kernel_share_of_step": roi_mean_ms / ms_per_step},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps},
+        "gpu_launches": hp.kernel_launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

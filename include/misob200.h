@@ -89,6 +89,11 @@ typedef struct {
     float spatial_scale[MB_MAX_LEVELS];
     float level_thresholds[MB_MAX_LEVELS];
     const float* features[MB_MAX_LEVELS]; /* device, NCHW contiguous */
+    /* Alternative RoI layout (the fused RPN stage's output): boxes_per_image > 0 means `rois`
+     * is [num_images, boxes_per_image, 4] and the batch index of row k is k / boxes_per_image;
+     * box_counts (device, nullable) gives the live rows per image, rows beyond it produce zeros. */
+    int32_t boxes_per_image;
+    const int32_t* box_counts;
 } mb_roi_align_params;
 size_t mb_roi_align_workspace_bytes(int64_t num_rois);
 int mb_multiscale_roi_align(const mb_roi_align_params* params_host, const float* rois, int64_t num_rois,
@@ -189,7 +194,8 @@ int mb_det_postprocess(const mb_det_params* params_host, const float* class_logi
  *   (x_begin, y_begin, width, height) after numpy slice resolution, xywh [N*cap, 4] fp32,
  *   src index [N*cap] int32 (n*cap + i), byte offsets [N*cap+1] int64 into the packed crop
  *   buffer, and totals[0] = number of crops, totals[1] = total bytes.
- * mb_crop_gather: copies the pixels. images: one uint8 HWC device pointer per image.
+ * mb_crop_gather: copies the pixels. images: one uint8 HWC device pointer per image. If
+ *   totals[1] exceeds crops_capacity_bytes nothing is copied and totals[2] is set to 1.
  * ------------------------------------------------------------------------------------ */
 typedef struct {
     int32_t num_images, capacity, channels;
@@ -201,7 +207,7 @@ int mb_crop_plan(const mb_crop_params* params_host, const float* det_boxes, cons
                  const int32_t* det_counts, int32_t* rects_out, float* xywh_out, int32_t* src_out,
                  int64_t* offsets_out, int64_t* totals_out, mb_stream_t stream);
 int mb_crop_gather(const mb_crop_params* params_host, const int32_t* rects, const int32_t* src,
-                   const int64_t* offsets, const int64_t* totals, uint8_t* crops_out,
+                   const int64_t* offsets, int64_t* totals, uint8_t* crops_out,
                    int64_t crops_capacity_bytes, mb_stream_t stream);
 
 #ifdef __cplusplus

@@ -1,4 +1,193 @@
-// placeholder — replaced by the real kernels (see include/misob200.h)
+// crop.cu — final score filter, annotation geometry and per-detection crop extraction.
+//
+// Replaces, on the device and without per-detection host round trips:
+//   ref:miso/object_detection/inference.py:53-62   scores > threshold (strict), x, y, w=x2-x1, h=y2-y1 (fp32)
+//   ref:miso/object_detection/dataset/annotation.py:120-127   coords = (x, y, x+w, y+h) in fp32;
+//                                                   coords_int = int(np.round(c)), round half to even
+//   ref:miso/object_detection/crop.py:28-30          crop = im[c[1]:c[3], c[0]:c[2], ...] (numpy slice rules)
+//
+//   k_crop_plan    one CTA: filter + rounding + slice resolution + stable compaction + byte offsets
+//   k_crop_gather  persistent grid (SM-count multiple): crop slots strided over blockIdx.x, rows over
+//                  blockIdx.y, lanes along the contiguous bytes of a source row (HWC uint8)
+#include <math.h>
+
 #include "common.cuh"
-extern "C" int mb_crop_plan(const mb_crop_params*, const float*, const float*, const int32_t*, int32_t*, float*, int32_t*, int64_t*, int64_t*, mb_stream_t) { return MB_ERR_UNSUPPORTED; }
-extern "C" int mb_crop_gather(const mb_crop_params*, const int32_t*, const int32_t*, const int64_t*, const int64_t*, uint8_t*, int64_t, mb_stream_t) { return MB_ERR_UNSUPPORTED; }
+
+namespace mb {
+
+struct CropDev {
+    int N, cap, ch;
+    float thr;
+    int h[MB_MAX_IMAGES], w[MB_MAX_IMAGES];
+    const unsigned char* img[MB_MAX_IMAGES];
+};
+
+// Python slice.indices(len) for step 1: returns begin and extent
+__device__ __forceinline__ void resolve_slice(long long start, long long stop, int len, int& begin, int& extent) {
+    if (start < 0) { start += len; if (start < 0) start = 0; } else if (start > len) start = len;
+    if (stop < 0) { stop += len; if (stop < 0) stop = 0; } else if (stop > len) stop = len;
+    begin = (int)start;
+    extent = stop > start ? (int)(stop - start) : 0;
+}
+
+__device__ __forceinline__ long long round_half_even_to_int(float v) {
+    // np.round on float32 rounds half to even and stays float32; int() then truncates an integer value
+    const float r = rintf(v);
+    if (!(r == r)) return 0;
+    if (r > 9.0e18f) return (long long)9.0e18;
+    if (r < -9.0e18f) return -(long long)9.0e18;
+    return (long long)r;
+}
+
+__global__ void __launch_bounds__(1024) k_crop_plan(const CropDev d, const float4* __restrict__ boxes,
+                                                   const float* __restrict__ scores, const int* __restrict__ counts,
+                                                   int4* __restrict__ rects, float4* __restrict__ xywh,
+                                                   int* __restrict__ src, long long* __restrict__ offsets,
+                                                   long long* __restrict__ totals) {
+    __shared__ int wcnt[32];
+    __shared__ long long wbytes[32];
+    __shared__ int s_cnt;
+    __shared__ long long s_bytes;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) { s_cnt = 0; s_bytes = 0; }
+    __syncthreads();
+    const int total = d.N * d.cap;
+    for (int e0 = 0; e0 < total; e0 += 1024) {
+        const int e = e0 + tid;
+        bool ok = false;
+        int4 rc = make_int4(0, 0, 0, 0);
+        float4 an = make_float4(0, 0, 0, 0);
+        long long nbytes = 0;
+        if (e < total) {
+            const int n = e / d.cap, i = e - n * d.cap;
+            if (i < counts[n] && scores[e] > d.thr) {
+                ok = true;
+                const float4 b = boxes[e];
+                an = make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+                const long long c0 = round_half_even_to_int(an.x), c1 = round_half_even_to_int(an.y);
+                const long long c2 = round_half_even_to_int(__fadd_rn(an.x, an.z));
+                const long long c3 = round_half_even_to_int(__fadd_rn(an.y, an.w));
+                resolve_slice(c0, c2, d.w[n], rc.x, rc.z);
+                resolve_slice(c1, c3, d.h[n], rc.y, rc.w);
+                nbytes = (long long)rc.z * rc.w * d.ch;
+            }
+        }
+        // stable compaction: exclusive scan of (flag, bytes) over the 1024 entries of this round
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        long long bs = nbytes;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, bs, o);
+            if (lane >= o) bs += y;
+        }
+        if (lane == 31) wbytes[wid] = bs;
+        if (lane == 0) wcnt[wid] = __popc(m);
+        __syncthreads();
+        int pc = 0, tc = 0;
+        long long pb = 0, tb = 0;
+        for (int q = 0; q < 32; ++q) {
+            pc += (q < wid) ? wcnt[q] : 0; tc += wcnt[q];
+            pb += (q < wid) ? wbytes[q] : 0; tb += wbytes[q];
+        }
+        const int base_c = s_cnt;
+        const long long base_b = s_bytes;
+        if (ok) {
+            const int j = base_c + pc + __popc(m & ((1u << lane) - 1));
+            rects[j] = rc;
+            xywh[j] = an;
+            src[j] = e;
+            offsets[j] = base_b + pb + bs - nbytes;
+        }
+        __syncthreads();
+        if (tid == 0) { s_cnt = base_c + tc; s_bytes = base_b + tb; }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        offsets[s_cnt] = s_bytes;
+        totals[0] = s_cnt;
+        totals[1] = s_bytes;
+        totals[2] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_crop_gather(const CropDev d, const int4* __restrict__ rects,
+                                                    const int* __restrict__ src, const long long* __restrict__ offsets,
+                                                    long long* __restrict__ totals, unsigned char* __restrict__ out,
+                                                    long long capacity) {
+    const long long ncrops = totals[0];
+    if (totals[1] > capacity) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) totals[2] = 1;  // caller re-runs with totals[1] bytes
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (long long j = blockIdx.x; j < ncrops; j += gridDim.x) {
+        const int4 rc = rects[j];
+        const int n = src[j] / d.cap;
+        const int row_bytes = rc.z * d.ch;
+        const unsigned char* im = d.img[n];
+        unsigned char* dst = out + offsets[j];
+        for (int y = blockIdx.y * nwarps + warp; y < rc.w; y += gridDim.y * nwarps) {
+            const unsigned char* s = im + ((size_t)(rc.y + y) * d.w[n] + rc.x) * d.ch;
+            unsigned char* o = dst + (size_t)y * row_bytes;
+            // head bytes up to 4-byte alignment of the destination, funnel-shifted words, tail bytes
+            const int head = min(row_bytes, (int)((4 - (reinterpret_cast<uintptr_t>(o) & 3)) & 3));
+            if (lane < head) o[lane] = __ldg(s + lane);
+            const int words = (row_bytes - head) >> 2;
+            const unsigned char* sw = s + head;
+            const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(sw) & 3) * 8;
+            const unsigned int* sa = reinterpret_cast<const unsigned int*>(sw - (shift >> 3));
+            unsigned int* oa = reinterpret_cast<unsigned int*>(o + head);
+            // the last source word may straddle the end of the image buffer: leave it to the byte tail
+            const int safe_words = shift ? max(words - 1, 0) : words;
+            for (int i = lane; i < safe_words; i += 32) {
+                const unsigned lo = __ldg(sa + i);
+                const unsigned hi = shift ? __ldg(sa + i + 1) : 0u;
+                oa[i] = shift ? __funnelshift_r(lo, hi, shift) : lo;
+            }
+            for (int i = head + safe_words * 4 + lane; i < row_bytes; i += 32) o[i] = __ldg(s + i);
+        }
+    }
+}
+
+static int make_crop(const mb_crop_params& p, CropDev& d, bool need_images) {
+    if (p.num_images < 1 || p.num_images > MB_MAX_IMAGES || p.capacity < 1 || p.channels < 1) return MB_ERR_INVALID_ARG;
+    d.N = p.num_images; d.cap = p.capacity; d.ch = p.channels; d.thr = p.threshold;
+    for (int n = 0; n < d.N; ++n) {
+        if (p.image_h[n] < 0 || p.image_w[n] < 0) return MB_ERR_INVALID_ARG;
+        d.h[n] = p.image_h[n]; d.w[n] = p.image_w[n]; d.img[n] = p.images[n];
+        if (need_images && !d.img[n]) return MB_ERR_INVALID_ARG;
+    }
+    return MB_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_crop_plan(const mb_crop_params* p, const float* det_boxes, const float* det_scores,
+                            const int32_t* det_counts, int32_t* rects_out, float* xywh_out, int32_t* src_out,
+                            int64_t* offsets_out, int64_t* totals_out, mb_stream_t stream) {
+    if (!p || !det_boxes || !det_scores || !det_counts || !rects_out || !xywh_out || !src_out || !offsets_out || !totals_out)
+        return MB_ERR_INVALID_ARG;
+    CropDev d;
+    int rc = make_crop(*p, d, false);
+    if (rc != MB_OK) return rc;
+    k_crop_plan<<<1, 1024, 0, (cudaStream_t)stream>>>(d, (const float4*)det_boxes, det_scores, det_counts, (int4*)rects_out,
+                                                      (float4*)xywh_out, src_out, (long long*)offsets_out, (long long*)totals_out);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
+
+extern "C" int mb_crop_gather(const mb_crop_params* p, const int32_t* rects, const int32_t* src, const int64_t* offsets,
+                              int64_t* totals, uint8_t* crops_out, int64_t crops_capacity_bytes, mb_stream_t stream) {
+    if (!p || !rects || !src || !offsets || !totals || crops_capacity_bytes < 0) return MB_ERR_INVALID_ARG;
+    if (crops_capacity_bytes > 0 && !crops_out) return MB_ERR_INVALID_ARG;
+    CropDev d;
+    int rc = make_crop(*p, d, true);
+    if (rc != MB_OK) return rc;
+    dim3 grid(kNumSMs, 8);
+    k_crop_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(d, (const int4*)rects, src, (const long long*)offsets,
+                                                         (long long*)totals, crops_out, crops_capacity_bytes);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}

@@ -97,7 +97,7 @@ struct MetaRule {
     float* seg_offset;      // [G] out
 };
 
-__global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, int compute_starts,
+static __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, int compute_starts,
                                                    long long mask_cap_words, MetaRule rule) {
     __shared__ long long sh[64];
     __shared__ long long carry[4];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, int compu
 constexpr int kRankThreads = 256;
 constexpr int kRankTile = 1024;
 
-__global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
+static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
     const unsigned long long* __restrict__ bkey, const float4* __restrict__ bbox,
     const int* __restrict__ bseg, const int* __restrict__ seg_start,
     const int* __restrict__ seg_count, const float* __restrict__ seg_offset, int P,
@@ -234,8 +234,15 @@ __device__ __forceinline__ bool iou_suppresses(const float4 a, const float area_
 // ------------------------------------------------------------------------------------
 // mask: persistent loop over upper-triangular 64x64 tiles of all segments
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
-                                                 float thr_up, unsigned long long* __restrict__ mask) {
+__device__ __forceinline__ float4 offset_box(float4 b, float o) {
+    return make_float4(__fadd_rn(b.x, o), __fadd_rn(b.y, o), __fadd_rn(b.z, o), __fadd_rn(b.w, o));
+}
+
+// seg_offset (nullable): per-segment coordinate offset of the batched_nms coordinate trick,
+// added on load (tv:ops/boxes.py:101); 0 for segments that run the per-group strategy.
+static __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
+                                                 float thr_up, unsigned long long* __restrict__ mask,
+                                                 const float* __restrict__ seg_offset) {
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     __shared__ int sh_g, sh_r, sh_c;
@@ -263,15 +270,16 @@ __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox
         const int g = sh_g, r = sh_r, c = sh_c;
         const int n = s.seg_count[g], T = s.seg_words[g], st = s.seg_start[g];
         const int ncol = min(64, n - c * 64);
+        const float off = seg_offset != nullptr ? seg_offset[g] : 0.0f;
         if (tid < ncol) {
-            const float4 b = sbox[st + c * 64 + tid];
+            const float4 b = offset_box(sbox[st + c * 64 + tid], off);
             cbox[tid] = b;
             carea[tid] = box_area_rn(b);
         }
         __syncthreads();
         const int row = r * 64 + tid;
         if (row < n) {
-            const float4 a = sbox[st + row];
+            const float4 a = offset_box(sbox[st + row], off);
             const float area_a = box_area_rn(a);
             unsigned long long word = 0;
             const int j0 = (r == c) ? tid + 1 : 0;
@@ -290,7 +298,7 @@ __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox
 // ------------------------------------------------------------------------------------
 constexpr int kSweepThreads = 256;
 
-__global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(SegArrays s, const unsigned long long* __restrict__ mask,
+static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(SegArrays s, const unsigned long long* __restrict__ mask,
                                                             unsigned long long* __restrict__ keepbits, int max_keep) {
     extern __shared__ unsigned long long removed[];
     __shared__ unsigned long long diag[64];
@@ -357,9 +365,9 @@ inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsi
 // Host helper: launch meta + mask + sweep on prepared sorted boxes.
 inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max_seg_elems, double iou_threshold,
                                  unsigned long long* mask, unsigned long long* keepbits, int max_keep,
-                                 cudaStream_t stream) {
+                                 cudaStream_t stream, const float* seg_offset = nullptr) {
     const float thr_up = strict_gt_threshold(iou_threshold);
-    k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask);
+    k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
     const int smem = sweep_smem_bytes(ceil_div(max_seg_elems, 64) + 1);
     if (smem > 48 * 1024) {

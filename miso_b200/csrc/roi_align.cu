@@ -35,7 +35,7 @@ struct Tap {       // one sample along one axis
 };
 
 struct RoiGeom {
-    int level, batch;
+    int level, batch;   // batch < 0: dead row (zeros)
     int H, W;
     float start_h, start_w, bin_h, bin_w;
     int grid_h, grid_w;
@@ -48,6 +48,20 @@ __device__ __forceinline__ int roi_level(const float* r, const mb_roi_align_para
     int lvl = 0;
     for (int i = 0; i + 1 < p.num_levels; ++i) lvl += (area >= p.level_thresholds[i]) ? 1 : 0;
     return lvl;
+}
+
+// row k of the RoI array as (batch, x1, y1, x2, y2) for either layout
+__device__ __forceinline__ void load_roi(const float* rois, long long k, const mb_roi_align_params& p, float r[5]) {
+    if (p.boxes_per_image > 0) {
+        const float4 b = reinterpret_cast<const float4*>(rois)[k];
+        const int n = (int)(k / p.boxes_per_image);
+        const bool live = p.box_counts == nullptr || (int)(k - (long long)n * p.boxes_per_image) < p.box_counts[n];
+        r[0] = live ? (float)n : -1.0f;
+        r[1] = b.x; r[2] = b.y; r[3] = b.z; r[4] = b.w;
+    } else {
+        const float* q = rois + k * 5;
+        r[0] = q[0]; r[1] = q[1]; r[2] = q[2]; r[3] = q[3]; r[4] = q[4];
+    }
 }
 
 __device__ __forceinline__ void roi_geometry(const float* r, const mb_roi_align_params& p, RoiGeom& g) {
@@ -105,13 +119,12 @@ __device__ __forceinline__ float bilinear4(float hy, float ly, float hx, float l
 }
 
 template <bool EXACT, bool SR2>
-__global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_align_params p,
+__global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_staged(const mb_roi_align_params p,
                                                                  const float* __restrict__ rois, int num_rois,
                                                                  float* __restrict__ out, int* __restrict__ levels_out,
                                                                  int stage_floats) {
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[kMaxSamples], xtab[kMaxSamples];
-    __shared__ RoiGeom geom;
     // sampling_ratio == 2: per output row / column, both samples packed for 128-bit broadcast loads
     __shared__ __align__(16) int4 yoff2[kMaxSamples / 2], xoff2[kMaxSamples / 2];
     __shared__ __align__(16) float4 ywt2[kMaxSamples / 2], xwt2[kMaxSamples / 2];
@@ -126,15 +139,11 @@ __global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_a
     float* patch = smem + kChunk * opitch;     // [kChunk][pitch]
     const int patch_floats = stage_floats - kChunk * opitch;
 
-    const float* r = rois + (size_t)k * 5;
-    if (tid == 0) {
-        RoiGeom g;
-        roi_geometry(r, p, g);
-        geom = g;
-        if (levels_out != nullptr && c0 == 0) levels_out[k] = g.level;
-    }
-    __syncthreads();
-    const RoiGeom g = geom;
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);  // every thread, in registers: cheaper than a broadcast through shared memory
+    if (levels_out != nullptr && c0 == 0 && tid == 0) levels_out[k] = g.level;
     const int ny = PH * g.grid_h, nx = PW * g.grid_w;
     if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid / g.grid_h, tid % g.grid_h, g.grid_h, g.H);
     if (tid >= 64 && tid < 64 + nx) {
@@ -144,10 +153,16 @@ __global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_a
     __syncthreads();
 
     const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
-    // footprint columns (all valid x samples)
+    // Footprint columns. Sample coordinates are monotone, so invalid samples sit at the two ends:
+    // the footprint runs from the first valid sample's low pixel to the last valid one's high pixel.
     int x0 = 0x7fffffff, x1 = -1;
-    for (int i = 0; i < nx; ++i)
-        if (xtab[i].valid) { x0 = min(x0, xtab[i].lo); x1 = max(x1, xtab[i].hi); }
+    {
+        int i = 0;
+        while (i < nx && !xtab[i].valid) ++i;
+        int j = nx - 1;
+        while (j >= 0 && !xtab[j].valid) --j;
+        if (i <= j) { x0 = xtab[i].lo; x1 = xtab[j].hi; }
+    }
     const int cols = x1 - x0 + 1;
     const int c = c0 + lane;
     const bool c_ok = c < p.channels;
@@ -163,6 +178,18 @@ __global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_a
         if (x1 < 0 || bad_batch) {
             ph1 = PH;  // nothing to sample: zeros
         } else {
+            if (ph0 == 0) {  // common case: the whole footprint fits the staging buffer
+                int i = 0;
+                while (i < ny && !ytab[i].valid) ++i;
+                int j = ny - 1;
+                while (j >= 0 && !ytab[j].valid) --j;
+                const int rows_a = (i <= j) ? ytab[j].hi - ytab[i].lo + 1 : 0;
+                const int pix_a = rows_a * cols;
+                if ((pix_a + ((33 - (pix_a & 31)) & 31)) * kChunk <= patch_floats) {
+                    ph1 = PH;
+                    if (rows_a > 0) { gy0 = ytab[i].lo; gy1 = ytab[j].hi; }
+                }
+            }
             while (ph1 < PH) {
                 int ny0 = gy0, ny1 = gy1;
                 for (int i = ph1 * g.grid_h; i < (ph1 + 1) * g.grid_h; ++i)
@@ -179,14 +206,47 @@ __global__ void __launch_bounds__(kRoiThreads) k_roi_align_staged(const mb_roi_a
         const int pix = rows * cols;
         const int pitch = pix + ((33 - (pix & 31)) & 31);
 
-        // ---- stage the footprint: warp per (channel,row), lanes along x (coalesced) ----
+        // ---- stage the footprint. Lanes run along x (coalesced); narrow footprints pack several
+        //      (channel,row) slots into one warp instruction; 8 independent loads are issued
+        //      before the first store so that one warp keeps 8 rows in flight. ----
         if (!direct && rows > 0) {
             const int nch = min(kChunk, p.channels - c0);
-            for (int cr = warp; cr < nch * rows; cr += kRoiWarps) {
-                const int cc = cr / rows, rr = cr - cc * rows;
-                const float* src = base + (size_t)cc * plane + (size_t)(gy0 + rr) * g.W + x0;
-                float* dst = patch + cc * pitch + rr * cols;
-                for (int x = lane; x < cols; x += 32) dst[x] = __ldg(src + x);
+            const int nslots = nch * rows;
+            if (cols <= 32) {
+                int cp2 = 1;
+                while (cp2 < cols) cp2 <<= 1;
+                const int rpi = 32 / cp2;                 // row slots per warp instruction
+                const int sub = lane / cp2, x = lane - sub * cp2;
+                const int step = kRoiWarps * rpi;         // slots per CTA iteration
+                const int dcc = step / rows, drr = step - dcc * rows;
+                int q = warp * rpi + sub;
+                int cc = q / rows, rr = q - cc * rows;
+                const float* src0 = base + (size_t)gy0 * g.W + x0 + x;
+                const bool xa = x < cols;
+                constexpr int U = 8;
+                for (int it = 0; it < nslots; it += step * U) {
+                    float v[U];
+                    int so[U];
+                    bool ok[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        ok[u] = xa && (q < nslots);
+                        so[u] = cc * pitch + rr * cols + x;
+                        if (ok[u]) v[u] = __ldg(src0 + (size_t)cc * plane + rr * g.W);
+                        q += step; cc += dcc; rr += drr;
+                        if (rr >= rows) { rr -= rows; ++cc; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (ok[u]) patch[so[u]] = v[u];
+                }
+            } else {
+                for (int cr = warp; cr < nslots; cr += kRoiWarps) {
+                    const int cc = cr / rows, rr = cr - cc * rows;
+                    const float* src = base + (size_t)cc * plane + (size_t)(gy0 + rr) * g.W + x0;
+                    float* dst = patch + cc * pitch + rr * cols;
+                    for (int x = lane; x < cols; x += 32) dst[x] = __ldg(src + x);
+                }
             }
         }
         if (SR2 && !direct && rows > 0) {
@@ -274,7 +334,8 @@ __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_par
         const int ph = (int)((idx / PW) % PH);
         const int c = (int)((idx / ((long long)PW * PH)) % p.channels);
         const long long k = idx / ((long long)PW * PH * p.channels);
-        const float* r = rois + k * 5;
+        float r[5];
+        load_roi(rois, k, p, r);
         RoiGeom g;
         roi_geometry(r, p, g);
         if (levels_out != nullptr && c == 0 && ph == 0 && pw == 0) levels_out[k] = g.level;

@@ -1,0 +1,87 @@
+"""Tiled mosaic path (BASELINE config 5): overlapping tiles sharded over the GPUs of one box,
+one NCCL all-gather of fixed-size detection blocks, then a cross-tile "seam" NMS.
+
+The reference has no counterpart (ref:miso/object_detection/inference.py:86-88 feeds whole
+images, which the model's transform shrinks to <= 1333 px); the semantics are DEFINED as the
+single-process composition of reference operations:
+
+    for every tile, row-major: detections of the tile (reference path) -> add the tile origin in
+    fp32 -> concatenate -> torchvision.ops.boxes._batched_nms_vanilla(boxes, scores, labels, iou)
+    -> miso's `score > threshold` filter (applied before the exchange; greedy NMS only lets
+    higher-scored boxes suppress lower-scored ones, so this does not change the result).
+
+Sharding: tiles in row-major order, contiguous blocks per rank, so concatenating the rank blocks
+in rank order reproduces the single-GPU tile order (deterministic tie-breaking for any world size).
+The only collective is one all_gather_into_tensor of [tiles_per_rank_max * dpi, 6] fp32 rows.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+
+def tile_starts(extent: int, tile: int, overlap: int) -> List[int]:
+    """Starts 0, stride, 2*stride, ... plus a clamped last tile (16384/1024/128 -> 19 starts)."""
+    if extent <= tile:
+        return [0]
+    stride = tile - overlap
+    starts = list(range(0, extent - tile, stride))
+    starts.append(extent - tile)
+    return starts
+
+
+def tile_grid(height: int, width: int, tile: int, overlap: int) -> List[Tuple[int, int]]:
+    """Row-major (y, x) origins."""
+    return [(y, x) for y in tile_starts(height, tile, overlap) for x in tile_starts(width, tile, overlap)]
+
+
+def rank_tiles(num_tiles: int, world: int, rank: int) -> range:
+    """Contiguous block of rank r: [floor(T*r/G), floor(T*(r+1)/G))."""
+    return range(num_tiles * rank // world, num_tiles * (rank + 1) // world)
+
+
+def tiles_per_rank_max(num_tiles: int, world: int) -> int:
+    return max(len(rank_tiles(num_tiles, world, r)) for r in range(world))
+
+
+def pack_block(det_boxes: Tensor, det_scores: Tensor, det_labels: Tensor, det_counts: Tensor, origins: Tensor,
+               threshold: float, rows: int) -> Tensor:
+    """[T, dpi, *] detections of this rank's tiles -> one fixed-size block [rows, 6] =
+    (x1, y1, x2, y2, score, label) in mosaic coordinates. Rows that hold no detection, or one
+    that fails `score > threshold`, get label -1. origins: [T, 2] = (y, x) as fp32 (exact)."""
+    t, dpi = det_scores.shape
+    idx = torch.arange(dpi, device=det_scores.device)[None, :]
+    live = (idx < det_counts[:, None]) & (det_scores > threshold)
+    off = torch.stack([origins[:, 1], origins[:, 0], origins[:, 1], origins[:, 0]], dim=1)[:, None, :]
+    boxes = det_boxes + off                      # fp32 add, rounded once (origins are exact integers)
+    lab = torch.where(live, det_labels.to(torch.float32), torch.full_like(det_scores, -1.0))
+    block = torch.cat([boxes, det_scores[..., None], lab[..., None]], dim=2).reshape(t * dpi, 6)
+    if block.shape[0] < rows:
+        pad = torch.zeros((rows - block.shape[0], 6), dtype=block.dtype, device=block.device)
+        pad[:, 5] = -1.0
+        block = torch.cat([block, pad], dim=0)
+    return block.contiguous()
+
+
+def exchange(block: Tensor, world: int, group=None) -> Tensor:
+    """The path's one collective: all-gather of the per-rank blocks, rank order preserved."""
+    if world == 1:
+        return block
+    import torch.distributed as dist
+    out = torch.empty((world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(out, block, group=group)
+    return out
+
+
+def seam_nms(gathered: Tensor, iou_threshold: float, nms_fn: Optional[Callable] = None):
+    """Cross-tile NMS over every live row, always the per-class ("vanilla") strategy on raw
+    mosaic coordinates. Returns (boxes, scores, labels) in (score desc, gathered order asc) order."""
+    if nms_fn is None:
+        from .ops import _batched_nms_vanilla as nms_fn
+    live = gathered[:, 5] >= 0
+    rows = gathered[live]                        # compaction: the step's one host sync
+    boxes, scores, labels = rows[:, :4].contiguous(), rows[:, 4].contiguous(), rows[:, 5].to(torch.int64)
+    keep = nms_fn(boxes, scores, labels, iou_threshold)
+    return boxes[keep], scores[keep], labels[keep]

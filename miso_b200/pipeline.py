@@ -1,0 +1,215 @@
+"""HotPath — the whole post-head detection path as one prepared, sync-free plan.
+
+One `step()` is what happens between the CNN heads and the saved particle crops for one batch
+(SURVEY.md §3.2 with the cuDNN/cuBLAS parts taken as inputs):
+
+    RPN head outputs ──► mb_rpn_proposals ──► proposals [N, R, 4] (+counts)
+    FPN features + proposals ──► mb_multiscale_roi_align ──► box features [N*R, C, 7, 7]
+    box-head outputs (class logits, box regression) + proposals ──► mb_det_postprocess ──► detections
+    detections + original uint8 images ──► mb_crop_plan / mb_crop_gather ──► packed crops
+
+All parameter structs, workspaces and outputs are created once; `step()` only enqueues kernels
+on the current stream (6 C-ABI calls, no allocation, no host synchronisation).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import CropParams, DetParams, MisoB200Error, RoiAlignParams, RpnParams
+from .detection import DetConfig, RpnConfig
+from .ops import _ptr, base_anchors, infer_scale, level_thresholds
+import math
+
+
+@dataclass
+class HotPathShapes:
+    num_images: int
+    padded_image_size: Tuple[int, int]           # network input after padding (anchor strides)
+    image_sizes: Sequence[Tuple[int, int]]       # per image, after resize, before padding
+    original_image_sizes: Sequence[Tuple[int, int]]
+    rpn_grids: Sequence[Tuple[int, int]]         # RPN head output sizes per level (incl. 'pool')
+    feature_grids: Sequence[Tuple[int, int]]     # pooler levels ('0'..'3')
+    channels: int = 256
+    num_classes: int = 3
+    pooled: int = 7
+    sampling_ratio: int = 2
+    image_channels: int = 3
+
+
+class HotPath:
+    def __init__(self, shapes: HotPathShapes, rpn: RpnConfig, det: DetConfig, threshold: float = 0.5,
+                 crop_capacity_bytes: int = 64 << 20, exact_roi_align: bool = True, device="cuda:0"):
+        self.lib = _lib.load()
+        self.s, self.dev = shapes, torch.device(device)
+        n, R = shapes.num_images, int(rpn.post_nms_top_n)
+        self.R, self.dpi = R, int(det.detections_per_img)
+        dev = self.dev
+        f32, i32, i64 = torch.float32, torch.int32, torch.int64
+        # ---- outputs / intermediates (fixed capacity, device-side counts) ----
+        self.proposals = torch.zeros((n, R, 4), dtype=f32, device=dev)
+        self.prop_scores = torch.zeros((n, R), dtype=f32, device=dev)
+        self.prop_counts = torch.zeros((n,), dtype=i32, device=dev)
+        self.box_features = torch.empty((n * R, shapes.channels, shapes.pooled, shapes.pooled), dtype=f32, device=dev)
+        self.det_boxes = torch.zeros((n, self.dpi, 4), dtype=f32, device=dev)
+        self.det_boxes_net = torch.zeros((n, self.dpi, 4), dtype=f32, device=dev)
+        self.det_scores = torch.zeros((n, self.dpi), dtype=f32, device=dev)
+        self.det_labels = torch.zeros((n, self.dpi), dtype=i64, device=dev)
+        self.det_counts = torch.zeros((n,), dtype=i32, device=dev)
+        cap = n * self.dpi
+        self.crop_rects = torch.zeros((cap, 4), dtype=i32, device=dev)
+        self.crop_xywh = torch.zeros((cap, 4), dtype=f32, device=dev)
+        self.crop_src = torch.zeros((cap,), dtype=i32, device=dev)
+        self.crop_offsets = torch.zeros((cap + 1,), dtype=i64, device=dev)
+        self.crop_totals = torch.zeros((4,), dtype=i64, device=dev)
+        self.crop_capacity = int(crop_capacity_bytes)
+        self.crop_pixels = torch.empty((self.crop_capacity,), dtype=torch.uint8, device=dev)
+
+        # ---- RPN params ----
+        p = RpnParams()
+        p.num_images, p.num_levels = n, len(shapes.rpn_grids)
+        for l, (gh, gw) in enumerate(shapes.rpn_grids):
+            base = base_anchors(rpn.sizes[l], rpn.aspect_ratios[l])
+            p.feat_h[l], p.feat_w[l], p.anchors_per_loc[l] = gh, gw, base.shape[0]
+            p.stride_h[l], p.stride_w[l] = shapes.padded_image_size[0] // gh, shapes.padded_image_size[1] // gw
+            for a in range(base.shape[0]):
+                for c in range(4):
+                    p.base_anchors[l][a][c] = float(base[a, c])
+        for i, (h, w) in enumerate(shapes.image_sizes):
+            p.image_h[i], p.image_w[i] = int(h), int(w)
+        p.pre_nms_top_n, p.post_nms_top_n = int(rpn.pre_nms_top_n), R
+        p.nms_thresh, p.score_thresh, p.min_size = float(rpn.nms_thresh), float(rpn.score_thresh), float(rpn.min_size)
+        p.wx, p.wy, p.ww, p.wh = (float(v) for v in rpn.weights)
+        p.bbox_xform_clip, p.trick_numel = float(rpn.bbox_xform_clip), int(rpn.trick_numel)
+        self.rpn_params = p
+        self.anchors_per_loc = [p.anchors_per_loc[l] for l in range(p.num_levels)]
+
+        # ---- RoIAlign params ----
+        q = RoiAlignParams()
+        q.num_levels, q.num_images, q.channels = len(shapes.feature_grids), n, shapes.channels
+        q.pooled_h = q.pooled_w = shapes.pooled
+        q.sampling_ratio, q.aligned, q.exact = shapes.sampling_ratio, 0, int(exact_roi_align)
+        max_h = max(s[0] for s in shapes.image_sizes); max_w = max(s[1] for s in shapes.image_sizes)
+        scales = [infer_scale((1, 1, gh, gw), (max_h, max_w)) for gh, gw in shapes.feature_grids]
+        k_min, k_max = int(-math.log2(scales[0])), int(-math.log2(scales[-1]))
+        thr = level_thresholds(k_min, k_max) if len(scales) > 1 else ()
+        for l, (gh, gw) in enumerate(shapes.feature_grids):
+            q.height[l], q.width[l], q.spatial_scale[l] = gh, gw, scales[l]
+        for i, t in enumerate(thr):
+            q.level_thresholds[i] = t
+        q.boxes_per_image = R
+        q.box_counts = self.prop_counts.data_ptr()
+        self.roi_params = q
+
+        # ---- detection params ----
+        d = DetParams()
+        d.num_images, d.num_classes, d.max_props_per_image, d.detections_per_img = n, shapes.num_classes, R, self.dpi
+        for i in range(n):
+            d.image_h[i], d.image_w[i] = (int(v) for v in shapes.image_sizes[i])
+            d.orig_h[i], d.orig_w[i] = (int(v) for v in shapes.original_image_sizes[i])
+        d.nms_thresh, d.score_thresh, d.min_size = float(det.nms_thresh), float(det.score_thresh), float(det.min_size)
+        d.wx, d.wy, d.ww, d.wh = (float(v) for v in det.weights)
+        d.bbox_xform_clip, d.trick_numel = float(det.bbox_xform_clip), int(det.trick_numel)
+        self.det_params = d
+
+        # ---- crop params ----
+        c = CropParams()
+        c.num_images, c.capacity, c.channels = n, self.dpi, shapes.image_channels
+        for i in range(n):
+            c.image_h[i], c.image_w[i] = (int(v) for v in shapes.original_image_sizes[i])
+        c.threshold = float(threshold)
+        self.crop_params = c
+
+        # ---- workspaces ----
+        nb = self.lib.mb_rpn_workspace_bytes(C.byref(p))
+        db = self.lib.mb_det_workspace_bytes(C.byref(d))
+        if nb == 0 or db == 0:
+            raise MisoB200Error("HotPath: configuration outside the implemented envelope")
+        self.rpn_ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
+        self.det_ws = torch.empty((db,), dtype=torch.uint8, device=dev)
+        self._keep: List[Tensor] = []
+        self.kernel_launches_per_step = 7 + 1 + 7 + 2   # rpn(6 kernels + sweep), roi_align, det, crop
+
+    # ------------------------------------------------------------------------------
+    def bind(self, objectness: Sequence[Tensor], deltas: Sequence[Tensor], features: Sequence[Tensor],
+             class_logits: Tensor, box_regression: Tensor, images: Sequence[Tensor]) -> None:
+        """Attach the (device-resident) inputs. objectness/deltas: RPN head outputs per level (NCHW);
+        features: pooler levels (NCHW); class_logits [N*R, C] / box_regression [N*R, 4C]: box-head
+        outputs for the proposal slots; images: original uint8 HWC images."""
+        self._keep = [*objectness, *deltas, *features, class_logits, box_regression, *images]
+        for t in self._keep:
+            if t.device.type != "cuda" or not t.is_contiguous():
+                raise MisoB200Error("HotPath.bind: inputs must be contiguous CUDA tensors")
+        for l, (o, dl) in enumerate(zip(objectness, deltas)):
+            self.rpn_params.objectness[l], self.rpn_params.deltas[l] = o.data_ptr(), dl.data_ptr()
+        for l, f in enumerate(features):
+            self.roi_params.features[l] = f.data_ptr()
+        for i, im in enumerate(images):
+            self.crop_params.images[i] = im.data_ptr()
+        self.class_logits, self.box_regression = class_logits, box_regression
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def rpn(self, st=None):
+        st = st or self._stream()
+        _lib.check(self.lib.mb_rpn_proposals(C.byref(self.rpn_params), _ptr(self.proposals), _ptr(self.prop_scores),
+                                             _ptr(self.prop_counts), None, _ptr(self.rpn_ws), self.rpn_ws.numel(), st),
+                   "mb_rpn_proposals")
+
+    def roi_align(self, st=None):
+        st = st or self._stream()
+        _lib.check(self.lib.mb_multiscale_roi_align(C.byref(self.roi_params), _ptr(self.proposals),
+                                                    self.s.num_images * self.R, _ptr(self.box_features), None, None, 0, st),
+                   "mb_multiscale_roi_align")
+
+    def detections(self, st=None):
+        st = st or self._stream()
+        _lib.check(self.lib.mb_det_postprocess(C.byref(self.det_params), _ptr(self.class_logits), _ptr(self.box_regression),
+                                               _ptr(self.proposals), _ptr(self.prop_counts), 0, _ptr(self.det_boxes),
+                                               _ptr(self.det_boxes_net), _ptr(self.det_scores), _ptr(self.det_labels),
+                                               _ptr(self.det_counts), _ptr(self.det_ws), self.det_ws.numel(), st),
+                   "mb_det_postprocess")
+
+    def crops(self, st=None):
+        st = st or self._stream()
+        cp = C.byref(self.crop_params)
+        _lib.check(self.lib.mb_crop_plan(cp, _ptr(self.det_boxes), _ptr(self.det_scores), _ptr(self.det_counts),
+                                         _ptr(self.crop_rects), _ptr(self.crop_xywh), _ptr(self.crop_src),
+                                         _ptr(self.crop_offsets), _ptr(self.crop_totals), st), "mb_crop_plan")
+        _lib.check(self.lib.mb_crop_gather(cp, _ptr(self.crop_rects), _ptr(self.crop_src), _ptr(self.crop_offsets),
+                                           _ptr(self.crop_totals), _ptr(self.crop_pixels), self.crop_capacity, st),
+                   "mb_crop_gather")
+
+    def step(self) -> None:
+        st = self._stream()
+        self.rpn(st)
+        self.roi_align(st)
+        self.detections(st)
+        self.crops(st)
+
+    # ------------------------------------------------------------------------------
+    def results(self):
+        """Read back one step's results (one sync): per-image detections that passed the score
+        filter, their annotation bounds and crop arrays."""
+        tot = self.crop_totals.tolist()
+        if tot[2]:
+            raise MisoB200Error(f"crop buffer too small: {tot[1]} bytes needed, {self.crop_capacity} available")
+        k = tot[0]
+        rects = self.crop_rects[:k].cpu().numpy(); xywh = self.crop_xywh[:k].cpu().numpy()
+        src = self.crop_src[:k].cpu().numpy(); offs = self.crop_offsets[:k + 1].cpu().numpy()
+        pix = self.crop_pixels[:tot[1]].cpu().numpy()
+        labels = self.det_labels.cpu().numpy().reshape(-1); scores = self.det_scores.cpu().numpy().reshape(-1)
+        ch = self.s.image_channels
+        out = [[] for _ in range(self.s.num_images)]
+        for j in range(k):
+            _, _, w, h = rects[j]
+            arr = pix[offs[j]:offs[j + 1]].reshape((h, w, ch) if ch > 1 else (h, w))
+            out[int(src[j]) // self.dpi].append({"xywh": xywh[j], "label": int(labels[src[j]]),
+                                                "score": float(scores[src[j]]), "crop": arr})
+        return out

@@ -1,0 +1,72 @@
+"""Synthetic inputs of the BASELINE.json configurations (random-init shapes, no datasets).
+
+Config 2 ("Faster R-CNN ResNet-50-FPN batch-4 inference, 1000 RPN proposals/image, post-proc +
+RoIAlign"): 1024^2 images resized to 800^2 by the model's transform, FPN pyramid 200/100/50/25/13
+x 256 channels, 3 anchors per location, 3 logits (Coccolith, Coccosphere + background), miso's
+300 detections per image (ref:miso/object_detection/models.py:9). Everything upstream of the
+hot path (backbone, RPN head, box head) is replaced by seeded random tensors of the right shape.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Tuple
+
+import torch
+
+from .detection import DetConfig, RpnConfig
+from .pipeline import HotPathShapes
+
+RPN_SIZES = ((32,), (64,), (128,), (256,), (512,))
+RPN_RATIOS = ((0.5, 1.0, 2.0),) * 5
+
+
+@dataclass
+class Workload:
+    name: str
+    shapes: HotPathShapes
+    rpn: RpnConfig
+    det: DetConfig
+    threshold: float
+    host: Dict[str, List[torch.Tensor]]   # pinned host tensors: objectness, deltas, features, logits, regression, images
+
+    def input_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for ts in self.host.values() for t in ts)
+
+
+def faster_rcnn_batch(num_images: int = 4, original: int = 1024, resized: int = 800, channels: int = 256,
+                      num_classes: int = 3, post_nms_top_n: int = 1000, detections_per_img: int = 300,
+                      threshold: float = 0.5, seed: int = 0, pin: bool = True) -> Workload:
+    g = torch.Generator().manual_seed(seed)
+    padded = -(-resized // 32) * 32
+    grids = [(padded // s, padded // s) for s in (4, 8, 16, 32)]
+    pool = (-(-grids[-1][0] // 2), -(-grids[-1][1] // 2))          # LastLevelMaxPool: kernel 1, stride 2
+    rpn_grids = grids + [pool]
+    n = num_images
+
+    def rn(*shape, scale=1.0):
+        t = torch.randn(*shape, generator=g) * scale
+        return t.pin_memory() if pin else t
+
+    host = {
+        "objectness": [rn(n, 3, gh, gw, scale=2.0) for gh, gw in rpn_grids],
+        "deltas": [rn(n, 12, gh, gw, scale=0.5) for gh, gw in rpn_grids],
+        "features": [rn(n, channels, gh, gw) for gh, gw in grids],
+        "class_logits": [rn(n * post_nms_top_n, num_classes, scale=3.0)],
+        "box_regression": [rn(n * post_nms_top_n, 4 * num_classes, scale=0.5)],
+        "images": [],
+    }
+    for _ in range(n):
+        im = torch.randint(0, 256, (original, original, 3), dtype=torch.uint8, generator=g)
+        host["images"].append(im.pin_memory() if pin else im)
+    shapes = HotPathShapes(num_images=n, padded_image_size=(padded, padded), image_sizes=[(resized, resized)] * n,
+                           original_image_sizes=[(original, original)] * n, rpn_grids=rpn_grids, feature_grids=grids,
+                           channels=channels, num_classes=num_classes)
+    rpn = RpnConfig(RPN_SIZES, RPN_RATIOS, pre_nms_top_n=1000, post_nms_top_n=post_nms_top_n)
+    det = DetConfig(detections_per_img=detections_per_img)
+    name = (f"Faster R-CNN R50-FPN post-head path, batch {n}, {original}^2 images -> {resized}^2, "
+            f"{post_nms_top_n} RPN proposals/img, {channels} ch, RoIAlign 7x7, {detections_per_img} dets/img")
+    return Workload(name, shapes, rpn, det, threshold, host)
+
+
+def to_device(w: Workload, device) -> Dict[str, List[torch.Tensor]]:
+    return {k: [t.to(device, non_blocking=True) for t in v] for k, v in w.host.items()}

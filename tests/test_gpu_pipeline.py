@@ -1,0 +1,112 @@
+"""The prepared sync-free plan (miso_b200.pipeline.HotPath) against the oracle composition of the
+same stages (oracle/pipeline.py). Each stage is also re-checked on the GPU path's own
+intermediate results, so a 1-ulp exp() difference upstream cannot hide a downstream bug."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import detection as D
+from oracle import miso_path as M
+from oracle import pipeline as ref_pipeline
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def build(n=2, original=320, resized=256, channels=16, post=200, dpi=50, seed=0, exact=True):
+    from miso_b200 import pipeline, workload
+    w = workload.faster_rcnn_batch(num_images=n, original=original, resized=resized, channels=channels,
+                                   post_nms_top_n=post, detections_per_img=dpi, seed=seed, pin=False)
+    hp = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=32 << 20,
+                          exact_roi_align=exact, device=DEV)
+    dev = workload.to_device(w, DEV)
+    hp.bind(dev["objectness"], dev["deltas"], dev["features"], dev["class_logits"][0], dev["box_regression"][0], dev["images"])
+    return w, hp
+
+
+def oracle_run(w):
+    h = {k: [t.numpy() for t in v] for k, v in w.host.items()}
+    return ref_pipeline.run(h["objectness"], h["deltas"], h["features"], h["class_logits"][0], h["box_regression"][0],
+                            h["images"], padded_image_size=w.shapes.padded_image_size, image_sizes=w.shapes.image_sizes,
+                            original_image_sizes=w.shapes.original_image_sizes, sizes=w.rpn.sizes,
+                            aspect_ratios=w.rpn.aspect_ratios, pre_nms_top_n=w.rpn.pre_nms_top_n,
+                            post_nms_top_n=w.rpn.post_nms_top_n, detections_per_img=w.det.detections_per_img,
+                            threshold=w.threshold), h
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_hot_path_matches_oracle_composition(seed):
+    w, hp = build(seed=seed)
+    hp.step()
+    torch.cuda.synchronize()
+    ref, h = oracle_run(w)
+    n, R, dpi = w.shapes.num_images, hp.R, hp.dpi
+    pc = hp.prop_counts.cpu().numpy()
+    dc = hp.det_counts.cpu().numpy()
+    res = hp.results()
+    for i in range(n):
+        # stage 1: proposals
+        assert pc[i] == len(ref[i]["proposals"])
+        gp = hp.proposals[i, :pc[i]].cpu().numpy()
+        assert cases.box_rel_err(gp, ref[i]["proposals"]) < 1e-5
+        # stage 2: RoIAlign, bit-exact on the GPU path's own proposals
+        gf = hp.box_features[i * R:i * R + pc[i]].cpu().numpy()
+        feats = D.multiscale_roi_align(h["features"], [gp if j == i else np.zeros((0, 4), np.float32) for j in range(n)],
+                                       w.shapes.image_sizes, 7, 2)
+        assert np.array_equal(gf, feats)
+        assert torch.count_nonzero(hp.box_features[i * R + pc[i]:(i + 1) * R]) == 0   # dead slots are zeros
+        # stage 3: detections
+        assert dc[i] == len(ref[i]["labels"])
+        assert np.array_equal(hp.det_labels[i, :dc[i]].cpu().numpy(), ref[i]["labels"])
+        assert cases.box_rel_err(hp.det_boxes[i, :dc[i]].cpu().numpy(), ref[i]["boxes"]) < 1e-5
+        assert np.max(np.abs(hp.det_scores[i, :dc[i]].cpu().numpy() - ref[i]["scores"])) < 1e-6
+        # stage 4: score filter + crops, bit-exact on the GPU path's own detections
+        kb, ks, kl, xywh, ci, crops = M.filter_and_crop(h["images"][i], hp.det_boxes[i, :dc[i]].cpu().numpy(),
+                                                        hp.det_scores[i, :dc[i]].cpu().numpy(),
+                                                        hp.det_labels[i, :dc[i]].cpu().numpy(), w.threshold)
+        assert len(res[i]) == len(crops)
+        for got, want, lab, xy in zip(res[i], crops, kl, xywh):
+            assert got["label"] == lab
+            assert np.array_equal(got["xywh"], xy)
+            assert got["crop"].shape == want.shape and np.array_equal(got["crop"], want)
+        assert len(res[i]) == len(ref[i]["crops"])
+
+
+def test_hot_path_is_deterministic_and_idempotent():
+    w, hp = build(seed=3)
+    hp.step(); torch.cuda.synchronize()
+    a = [t.clone() for t in (hp.proposals, hp.box_features, hp.det_boxes, hp.det_labels, hp.crop_totals)]
+    pix = hp.crop_pixels[: int(hp.crop_totals[1])].clone()
+    for _ in range(3):
+        hp.step()
+    torch.cuda.synchronize()
+    for x, y in zip(a, (hp.proposals, hp.box_features, hp.det_boxes, hp.det_labels, hp.crop_totals)):
+        assert torch.equal(x, y)
+    assert torch.equal(pix, hp.crop_pixels[: int(hp.crop_totals[1])])
+
+
+def test_hot_path_full_size_config2_properties():
+    """BASELINE config 2 at full size (batch 4, 800^2, 256 ch, 1000 proposals): size-independent
+    properties — proposal scores sorted, NMS idempotence (re-running NMS on the kept proposals keeps
+    all of them), kept proposals inside the image, crops consistent with their rectangles."""
+    from miso_b200 import ops
+    w, hp = build(n=4, original=1024, resized=800, channels=256, post=1000, dpi=300, seed=0)
+    hp.step(); torch.cuda.synchronize()
+    pc = hp.prop_counts.cpu().numpy()
+    assert (pc == 1000).all()
+    for i in range(4):
+        s = hp.prop_scores[i, :pc[i]]
+        assert torch.all(s[:-1] >= s[1:])
+        b = hp.proposals[i, :pc[i]]
+        assert b.min() >= 0 and b.max() <= 800
+    tot = hp.crop_totals.tolist()
+    assert tot[2] == 0 and tot[0] > 0
+    offs = hp.crop_offsets[: tot[0] + 1].cpu().numpy(); rects = hp.crop_rects[: tot[0]].cpu().numpy()
+    assert np.array_equal(np.diff(offs), rects[:, 2].astype(np.int64) * rects[:, 3] * 3)
+    # detections: NMS idempotence per image and class on the network-scale boxes
+    dc = hp.det_counts.cpu().numpy()
+    for i in range(4):
+        keep = ops.batched_nms(hp.det_boxes_net[i, :dc[i]], hp.det_scores[i, :dc[i]], hp.det_labels[i, :dc[i]], 0.5,
+                               strategy="vanilla")
+        assert keep.numel() == dc[i]

@@ -323,6 +323,193 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_staged(const mb_ro
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// sampling_ratio == 2 (the detection models): CTA = one RoI, all channels.
+// Geometry, tap tables, footprint groups and a per-bin table of 16 (offset, weight) pairs are
+// built ONCE per RoI; the CTA then walks the channel chunks: stage 32 planes of the footprint
+// (thread = footprint pixel, loop over channels: one pointer increment per element, 8 loads in
+// flight), 49 bins x 32 channels from shared memory (8 broadcast LDS.128 of the bin's table +
+// 16 conflict-free LDS, products and sums in the reference's order), coalesced float4 write-out.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxGroups = 32;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_align_params p,
+                                                                const float* __restrict__ rois,
+                                                                float* __restrict__ out, int* __restrict__ levels_out,
+                                                                int patch_floats) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ Tap ytab[kMaxSamples], xtab[kMaxSamples];
+    __shared__ int grp_ph0[kMaxGroups + 1], grp_y0[kMaxGroups], grp_rows[kMaxGroups], grp_direct[kMaxGroups];
+    __shared__ int s_ngroups;
+
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
+    const int opitch = (nbins & 1) ? nbins : nbins + 1;
+    float* out_s = smem;                                   // [kChunk][opitch]
+    float* patch = out_s + kChunk * opitch;                // [kChunk][pitch]
+    int4* tab_off = reinterpret_cast<int4*>(patch + patch_floats);       // [nbins][4] (16-byte aligned by construction)
+    float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);      // [nbins][4]
+
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);
+    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
+    const int ny = PH * 2, nx = PW * 2;
+    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
+    if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
+    __syncthreads();
+
+    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
+    int x0 = 0, x1 = -1;
+    {
+        int i = 0;
+        while (i < nx && !xtab[i].valid) ++i;
+        int j = nx - 1;
+        while (j >= 0 && !xtab[j].valid) --j;
+        if (i <= j) { x0 = xtab[i].lo; x1 = xtab[j].hi; }
+    }
+    const int cols = x1 - x0 + 1;
+    const bool empty = bad_batch || x1 < 0;
+
+    // ---- footprint groups: maximal runs of output rows whose rows x cols fit the staging buffer ----
+    if (tid == 0) {
+        int ng = 0, ph0 = 0;
+        while (ph0 < PH && !empty) {
+            int gy0 = 0x7fffffff, gy1 = -1, ph1 = ph0;
+            while (ph1 < PH) {
+                int ny0 = gy0, ny1 = gy1;
+                for (int i = ph1 * 2; i < ph1 * 2 + 2; ++i)
+                    if (ytab[i].valid) { ny0 = min(ny0, ytab[i].lo); ny1 = max(ny1, ytab[i].hi); }
+                const int pix = (ny1 >= 0 ? ny1 - ny0 + 1 : 0) * cols;
+                if ((pix + ((33 - (pix & 31)) & 31)) * kChunk > patch_floats) break;
+                gy0 = ny0; gy1 = ny1; ++ph1;
+            }
+            const bool direct = (ph1 == ph0);
+            if (direct) {  // one output row alone does not fit: gather it straight from global memory
+                ph1 = ph0 + 1;
+                for (int i = ph0 * 2; i < ph0 * 2 + 2; ++i)
+                    if (ytab[i].valid) { gy0 = min(gy0, ytab[i].lo); gy1 = max(gy1, ytab[i].hi); }
+            }
+            grp_ph0[ng] = ph0; grp_y0[ng] = gy1 >= 0 ? gy0 : 0; grp_rows[ng] = gy1 >= 0 ? gy1 - gy0 + 1 : 0;
+            grp_direct[ng] = direct;
+            ++ng; ph0 = ph1;
+        }
+        grp_ph0[ng] = PH;
+        s_ngroups = ng;
+    }
+    __syncthreads();
+    const int ngroups = s_ngroups;
+
+    // ---- per-bin tables: 4 samples x 4 corners, offsets relative to the bin's group footprint ----
+    for (int e = tid; e < nbins * 4 && !empty; e += kRoiThreads) {
+        const int b = e >> 2, smp = e & 3;
+        const int ph = b / PW, pw = b - ph * PW;
+        int gi = 0;
+        while (gi + 1 < ngroups && ph >= grp_ph0[gi + 1]) ++gi;
+        const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
+        const bool ok = Y.valid && X.valid;
+        const bool direct = grp_direct[gi] != 0;
+        const int rs = direct ? g.W : cols;                 // row stride of the addressed buffer
+        const int oy = direct ? 0 : grp_y0[gi], ox = direct ? 0 : x0;
+        const int ylo = ok ? (Y.lo - oy) * rs : 0, yhi = ok ? (Y.hi - oy) * rs : 0;
+        const int xlo = ok ? X.lo - ox : 0, xhi = ok ? X.hi - ox : 0;
+        tab_off[e] = make_int4(ylo + xlo, ylo + xhi, yhi + xlo, yhi + xhi);
+        tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    const size_t plane = (size_t)g.H * g.W;
+    const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
+    const int nchunks = (p.channels + kChunk - 1) / kChunk;
+    float* dst_roi = out + (size_t)k * p.channels * nbins;
+
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int c0 = chunk * kChunk;
+        const int nch = min(kChunk, p.channels - c0);
+        const float* base = feat + (size_t)c0 * plane;
+        if (empty) {
+            for (int i = tid; i < kChunk * opitch; i += kRoiThreads) out_s[i] = 0.0f;
+            __syncthreads();
+        }
+        for (int gi = 0; gi < ngroups; ++gi) {
+            const int rows = grp_rows[gi], gy0 = grp_y0[gi];
+            const bool direct = grp_direct[gi] != 0;
+            const int P = rows * cols;
+            const int pitch = P + ((33 - (P & 31)) & 31);
+            // ---- stage: thread = footprint pixel (x fastest => coalesced rows), loop over channels ----
+            if (!direct && P > 0) {
+                const int NG = P <= kRoiThreads ? kRoiThreads / P : 1;   // channel groups running in parallel
+                for (int pos0 = 0; pos0 < P; pos0 += kRoiThreads) {
+                    int pos = pos0 + tid, grp = 0;
+                    if (NG > 1) { grp = tid / P; pos = tid - grp * P; }
+                    if (pos < P && grp < NG) {
+                        const int rr = pos / cols, x = pos - rr * cols;
+                        const float* src = base + (size_t)grp * plane + (size_t)(gy0 + rr) * g.W + x0 + x;
+                        float* dp = patch + grp * pitch + pos;
+                        const size_t sstep = (size_t)NG * plane;
+                        const int dstep = NG * pitch;
+                        int cc = grp;
+                        for (; cc + 7 * NG < nch; cc += 8 * NG) {
+                            float v[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u * sstep);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) dp[u * dstep] = v[u];
+                            src += 8 * sstep; dp += 8 * dstep;
+                        }
+                        for (; cc < nch; cc += NG) { *dp = __ldg(src); src += sstep; dp += dstep; }
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- bins of this group: warp per bin, lane per channel ----
+            const int b0 = grp_ph0[gi] * PW, b1 = grp_ph0[gi + 1] * PW;
+            const float* sp = direct ? (base + (size_t)lane * plane) : (patch + lane * pitch);
+            if (!direct && P == 0) {            // no valid sample row in this group: zeros (nothing was staged)
+                for (int b = b0 + warp; b < b1; b += kRoiWarps) out_s[lane * opitch + b] = 0.0f;
+            } else if (lane < nch) {
+                for (int b = b0 + warp; b < b1; b += kRoiWarps) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int smp = 0; smp < 4; ++smp) {
+                        const int4 o = tab_off[b * 4 + smp];
+                        const float4 wv = tab_w[b * 4 + smp];
+                        const float v1 = sp[o.x], v2 = sp[o.y], v3 = sp[o.z], v4 = sp[o.w];
+                        if (EXACT) {
+                            float t = __fmul_rn(wv.x, v1);
+                            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
+                            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
+                            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
+                            acc = __fadd_rn(acc, t);
+                        } else {
+                            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
+                        }
+                    }
+                    out_s[lane * opitch + b] = __fmul_rn(acc, 0.25f);   // acc / 4: exact scaling
+                }
+            }
+            __syncthreads();
+        }
+        // ---- write out: contiguous nch*nbins floats of out[k, c0:c0+nch] ----
+        float* dst = dst_roi + (size_t)c0 * nbins;
+        const int total = nch * nbins;
+        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(out_s);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = tid; i < total / 4; i += kRoiThreads) d4[i] = s4[i];
+        } else {
+            for (int ch = warp; ch < nch; ch += kRoiWarps)
+                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = out_s[ch * opitch + b];
+        }
+        // the next chunk's bins overwrite out_s only after its own staging barrier, which every
+        // thread reaches after finishing this copy
+    }
+}
+
 // Direct kernel: any sampling_ratio (incl. adaptive), any pooled size. One thread per output.
 __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_params p, const float* __restrict__ rois,
                                                          long long total, float* __restrict__ out,
@@ -382,6 +569,21 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     const bool staged = p.sampling_ratio > 0 && p.sampling_ratio * p.pooled_h <= kMaxSamples &&
                         p.sampling_ratio * p.pooled_w <= kMaxSamples && nbins <= 512 &&
                         num_rois * chunks < (1ll << 31);
+    if (staged && p.sampling_ratio == 2 && nbins <= 256 && num_rois < (1ll << 31)) {
+        const int opitch = (nbins & 1) ? nbins : nbins + 1;
+        const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
+        const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
+        if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
+        if (p.exact) {
+            MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_roi_align_sr2<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+        } else {
+            MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_roi_align_sr2<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+        }
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     if (staged) {
         // staging buffer: outputs + a footprint of up to ~320 pixels per channel (4 CTAs/SM at 7x7)
         const int opitch = (nbins & 1) ? nbins : nbins + 1;

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
     (void)sort_cap;
 }
 
-static int make_dev(const mb_rpn_params& p, RpnDev& d, RpnImages& im) {
+static int make_dev(const mb_rpn_params& p, RpnDev& d, RpnImages& im, bool need_ptrs) {
     if (p.num_images < 1 || p.num_images > MB_MAX_IMAGES || p.num_levels < 1 || p.num_levels > MB_MAX_LEVELS)
         return MB_ERR_INVALID_ARG;
     if (p.pre_nms_top_n < 1 || p.post_nms_top_n < 1) return MB_ERR_INVALID_ARG;
@@ -347,7 +347,7 @@ static int make_dev(const mb_rpn_params& p, RpnDev& d, RpnImages& im) {
         d.koff[l + 1] = d.koff[l] + d.k[l];
         d.boff[l + 1] = d.boff[l] + ceil_div(d.AL[l], kRpnChunk);
         d.obj[l] = p.objectness[l]; d.dlt[l] = p.deltas[l];
-        if (!d.obj[l] || !d.dlt[l]) return MB_ERR_INVALID_ARG;
+        if (need_ptrs && (!d.obj[l] || !d.dlt[l])) return MB_ERR_INVALID_ARG;
         for (int a = 0; a < d.A[l]; ++a)
             d.base[l][a] = make_float4(p.base_anchors[l][a][0], p.base_anchors[l][a][1], p.base_anchors[l][a][2], p.base_anchors[l][a][3]);
     }
@@ -366,7 +366,7 @@ using namespace mb;
 extern "C" size_t mb_rpn_workspace_bytes(const mb_rpn_params* p) {
     if (!p) return 0;
     RpnDev d; RpnImages im;
-    if (make_dev(*p, d, im) != MB_OK) return 0;
+    if (make_dev(*p, d, im, false) != MB_OK) return 0;
     Carver c(nullptr, 0);
     RpnScratch w;
     carve_rpn(c, w, d);
@@ -378,7 +378,7 @@ extern "C" int mb_rpn_proposals(const mb_rpn_params* p, float* proposals_out, fl
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!p || !proposals_out || !scores_out || !counts_out) return MB_ERR_INVALID_ARG;
     RpnDev d; RpnImages im;
-    int rc = make_dev(*p, d, im);
+    int rc = make_dev(*p, d, im, true);
     if (rc != MB_OK) return rc;
     Carver c(workspace, workspace_bytes);
     RpnScratch w;

@@ -74,3 +74,24 @@ def test_cpu_tensor_raises_instead_of_falling_back():
         ops.roi_align(torch.zeros(1, 1, 4, 4), torch.zeros(1, 5), 2)
     with pytest.raises(ValueError):
         ops.box_convert(torch.zeros(1, 4), "xyxy", "bogus")
+
+
+def test_workspace_queries_need_no_device_pointers(lib_path):
+    """Workspace sizing is host arithmetic: it must work before any input is bound."""
+    import ctypes as C
+    from miso_b200 import _lib
+    lib = _lib.load()
+    p = _lib.RpnParams()
+    p.num_images, p.num_levels = 4, 5
+    for l, g in enumerate((200, 100, 50, 25, 13)):
+        p.feat_h[l] = p.feat_w[l] = g
+        p.anchors_per_loc[l] = 3
+        p.stride_h[l] = p.stride_w[l] = 800 // g
+    p.pre_nms_top_n = p.post_nms_top_n = 1000
+    assert lib.mb_rpn_workspace_bytes(C.byref(p)) > 4 * 159882 * 8
+    p.pre_nms_top_n = 5000                      # outside the envelope -> 0, the host raises
+    assert lib.mb_rpn_workspace_bytes(C.byref(p)) == 0
+    d = _lib.DetParams()
+    d.num_images, d.num_classes, d.max_props_per_image, d.detections_per_img = 4, 3, 1000, 300
+    assert lib.mb_det_workspace_bytes(C.byref(d)) > 0
+    assert lib.mb_nms_workspace_bytes(200000, 80) > 200000 * 60

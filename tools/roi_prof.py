@@ -1,0 +1,26 @@
+"""RoIAlign only, BASELINE config 2 stress shapes — the program profiled with ncu."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from miso_b200 import ops  # noqa: E402
+from tests import cases  # noqa: E402
+
+DEV = "cuda:0"
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+per = 1000 if P == 7 else 100
+n = 4 if P == 7 else 8
+exact = (sys.argv[2] != "fast") if len(sys.argv) > 2 else True
+rng = np.random.default_rng(0)
+feats = [torch.randn(n, 256, 800 // s, 800 // s, device=DEV) for s in (4, 8, 16, 32)]
+boxes = [torch.from_numpy(cases.stress_rois(rng, per, (800, 800))).to(DEV) for _ in range(n)]
+pool = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], P, 2, exact=exact)
+x = {str(i): f for i, f in enumerate(feats)}
+for _ in range(3):
+    out = pool(x, boxes, [(800, 800)] * n)
+torch.cuda.synchronize()
+print("ok", out.shape, float(out.abs().mean()))

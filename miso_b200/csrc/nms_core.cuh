@@ -282,9 +282,24 @@ static __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict
             const float4 a = offset_box(sbox[st + row], off);
             const float area_a = box_area_rn(a);
             unsigned long long word = 0;
-            const int j0 = (r == c) ? tid + 1 : 0;
-            for (int j = j0; j < ncol; ++j)
-                if (iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1ull << j;
+            // Diagonal tiles carry the full symmetric word (bits j < tid too): the sweep resolves a
+            // 64-box block in parallel from "who suppresses me" = word & lower bits.
+            const int skip = (r == c) ? tid : -1;
+            if (thr_up > 0.0f) {
+                // an IoU above a positive threshold needs a positive intersection: most pairs are
+                // disjoint and never reach the division
+                for (int j = 0; j < ncol; ++j) {
+                    const float4 b = cbox[j];
+                    const float xx1 = (a.x < b.x) ? b.x : a.x, yy1 = (a.y < b.y) ? b.y : a.y;
+                    const float xx2 = (b.z < a.z) ? b.z : a.z, yy2 = (b.w < a.w) ? b.w : a.w;
+                    if (xx2 > xx1 && yy2 > yy1 && j != skip &&
+                        iou_suppresses(a, area_a, b, carea[j], thr_up))
+                        word |= 1ull << j;
+                }
+            } else {
+                for (int j = 0; j < ncol; ++j)
+                    if (j != skip && iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1ull << j;
+            }
             mask[s.mask_off[g] + (long long)row * T + c] = word;
         }
         __syncthreads();
@@ -360,6 +375,100 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(SegArrays s,
     if (tid == 0) s.seg_kept[g] = kept;
 }
 
+// ------------------------------------------------------------------------------------
+// sweep for segments of up to 4096 boxes (T <= 64 words): the 64 x (T-b) tile of mask words of
+// block b is staged in shared memory (next tile prefetched into registers while the current one
+// is resolved); one warp resolves the block in parallel: box t is kept iff every earlier box of
+// the block that overlaps it ("suppressors", the lower bits of its diagonal word) is removed, and
+// removed iff one of them is kept — the lowest undecided box is always decidable, so the
+// fixed point is reached in as many rounds as the longest suppression chain (typically 2-4);
+// kept rows are then OR-ed into removed[] by 256 threads with shared-memory atomics.
+// ------------------------------------------------------------------------------------
+constexpr int kSweepSmallMaxWords = 64;
+
+static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_small(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                                        unsigned long long* __restrict__ keepbits, int max_keep) {
+    __shared__ unsigned long long removed[kSweepSmallMaxWords];
+    __shared__ unsigned long long tile[64 * kSweepSmallMaxWords];
+    __shared__ unsigned long long s_keepw;
+    constexpr int kPre = 64 * kSweepSmallMaxWords / kSweepThreads;   // tile words per thread
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = s.seg_count[g];
+    const int T = s.seg_words[g];
+    if (n == 0 || s.totals[2] != 0) { if (tid == 0) s.seg_kept[g] = 0; return; }
+    const unsigned long long* m = mask + s.mask_off[g];
+    unsigned long long* kb = keepbits + s.keep_off[g];
+    if (tid < T) removed[tid] = 0;
+    unsigned long long pre[kPre];
+    // tile of block b: rows 64b .. 64b+nb-1, words b .. T-1, row-major with Wn = T - b words per row
+    auto prefetch = [&](int b) {
+        const int nb = min(64, n - b * 64), Wn = T - b;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            const int idx = tid + u * kSweepThreads;
+            pre[u] = 0;
+            if (idx < nb * Wn) {
+                const int row = idx / Wn, col = idx - row * Wn;
+                pre[u] = m[(long long)(b * 64 + row) * T + b + col];
+            }
+        }
+    };
+    prefetch(0);
+    int kept = 0;
+    for (int b = 0; b < T; ++b) {
+        const int nb = min(64, n - b * 64), Wn = T - b;
+#pragma unroll
+        for (int u = 0; u < kPre; ++u) {
+            const int idx = tid + u * kSweepThreads;
+            if (idx < nb * Wn) tile[idx] = pre[u];
+        }
+        __syncthreads();
+        if (b + 1 < T) prefetch(b + 1);          // global loads of the next tile fly during the resolve
+        if (warp == 0) {
+            const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
+            unsigned long long R = removed[b] | invalid, C = 0;
+            const int t0 = lane, t1 = lane + 32;
+            const unsigned long long s0 = (t0 < nb) ? (tile[t0 * Wn] & ((1ull << t0) - 1ull)) : 0ull;
+            const unsigned long long s1 = (t1 < nb) ? (tile[t1 * Wn] & ((1ull << t1) - 1ull)) : 0ull;
+            while ((C | R) != ~0ull) {
+                const unsigned long long D = C | R;
+                bool c0 = false, r0 = false, c1 = false, r1 = false;
+                if (!((D >> t0) & 1ull)) { if (s0 & C) r0 = true; else if ((s0 & ~R) == 0ull) c0 = true; }
+                if (!((D >> t1) & 1ull)) { if (s1 & C) r1 = true; else if ((s1 & ~R) == 0ull) c1 = true; }
+                C |= (unsigned long long)__ballot_sync(0xffffffffu, c0) | ((unsigned long long)__ballot_sync(0xffffffffu, c1) << 32);
+                R |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+            }
+            unsigned long long keepw = C;
+            if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
+                int extra = kept + __popcll(keepw) - max_keep;
+                while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+            }
+            if (lane == 0) { s_keepw = keepw; kb[b] = keepw; }
+        }
+        __syncthreads();
+        const unsigned long long keepw = s_keepw;
+        kept += __popcll(keepw);
+        if (max_keep > 0 && kept >= max_keep) {
+            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
+            break;
+        }
+        // removed[b + col] |= OR of the kept rows' words: thread = (column, quarter of the rows)
+        {
+            const int col = 1 + (tid >> 2), q = tid & 3;
+            if (col < Wn) {
+                unsigned long long acc = 0, bits = (keepw >> (16 * q)) & 0xffffull;
+                while (bits) {
+                    const int t = __ffsll((long long)bits) - 1 + 16 * q; bits &= bits - 1;
+                    acc |= tile[t * Wn + col];
+                }
+                if (acc) atomicOr(&removed[b + col], acc);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s.seg_kept[g] = kept;
+}
+
 inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsigned long long); }
 
 // Host helper: launch meta + mask + sweep on prepared sorted boxes.
@@ -369,6 +478,11 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     const float thr_up = strict_gt_threshold(iou_threshold);
     k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
+    if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {
+        k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     const int smem = sweep_smem_bytes(ceil_div(max_seg_elems, 64) + 1);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;

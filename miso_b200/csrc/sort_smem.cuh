@@ -18,7 +18,7 @@ __device__ inline void bitonic_sort_smem(unsigned long long* a, int n) {
             __syncthreads();
             for (int i = tid; i < (n >> 1); i += nt) {
                 // i-th compare-exchange pair of this stage
-                const int lo = ((i / j) * (j << 1)) + (i % j);
+                const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));   // j is a power of two
                 const int hi = lo + j;
                 const bool up = ((lo & k) == 0);
                 const unsigned long long x = a[lo], y = a[hi];

@@ -202,6 +202,7 @@ typedef struct {
     int32_t image_h[MB_MAX_IMAGES], image_w[MB_MAX_IMAGES];
     const uint8_t* images[MB_MAX_IMAGES]; /* device, HWC uint8, row pitch = w*channels */
     float threshold;
+    int32_t boxes_are_xywh; /* != 0: det_boxes rows already are annotation bounds (x, y, w, h) */
 } mb_crop_params;
 int mb_crop_plan(const mb_crop_params* params_host, const float* det_boxes, const float* det_scores,
                  const int32_t* det_counts, int32_t* rects_out, float* xywh_out, int32_t* src_out,

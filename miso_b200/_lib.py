@@ -71,7 +71,7 @@ class CropParams(C.Structure):
         ("num_images", _i32), ("capacity", _i32), ("channels", _i32),
         ("image_h", _i32 * MB_MAX_IMAGES), ("image_w", _i32 * MB_MAX_IMAGES),
         ("images", _p * MB_MAX_IMAGES),
-        ("threshold", _f32),
+        ("threshold", _f32), ("boxes_are_xywh", _i32),
     ]
 
 

@@ -35,6 +35,20 @@ __device__ __forceinline__ uint32_t desc_score_key(float s) {
     return ~asc;  // >= 0x007FFFFF for +inf, so 0 is reserved for NaN
 }
 
+// Warp-aggregated slot allocation: one atomic per warp instead of one per lane. Every lane of the
+// warp must call it (pred says whether this lane wants a slot); returns the lane's slot.
+template <typename CounterT>
+__device__ __forceinline__ int warp_alloc_slot(CounterT* counter, bool pred) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
 // Bump allocator over a caller-provided workspace.
 struct Carver {
     char* base;

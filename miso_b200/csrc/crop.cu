@@ -16,7 +16,7 @@
 namespace mb {
 
 struct CropDev {
-    int N, cap, ch;
+    int N, cap, ch, xywh;
     float thr;
     int h[MB_MAX_IMAGES], w[MB_MAX_IMAGES];
     const unsigned char* img[MB_MAX_IMAGES];
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(1024) k_crop_plan(const CropDev d, const float
             if (i < counts[n] && scores[e] > d.thr) {
                 ok = true;
                 const float4 b = boxes[e];
-                an = make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+                an = d.xywh ? b : make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
                 const long long c0 = round_half_even_to_int(an.x), c1 = round_half_even_to_int(an.y);
                 const long long c2 = round_half_even_to_int(__fadd_rn(an.x, an.z));
                 const long long c3 = round_half_even_to_int(__fadd_rn(an.y, an.w));
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_crop_gather(const CropDev d, const int4
 
 static int make_crop(const mb_crop_params& p, CropDev& d, bool need_images) {
     if (p.num_images < 1 || p.num_images > MB_MAX_IMAGES || p.capacity < 1 || p.channels < 1) return MB_ERR_INVALID_ARG;
-    d.N = p.num_images; d.cap = p.capacity; d.ch = p.channels; d.thr = p.threshold;
+    d.N = p.num_images; d.cap = p.capacity; d.ch = p.channels; d.thr = p.threshold; d.xywh = p.boxes_are_xywh;
     for (int n = 0; n < d.N; ++n) {
         if (p.image_h[n] < 0 || p.image_w[n] < 0) return MB_ERR_INVALID_ARG;
         d.h[n] = p.image_h[n]; d.w[n] = p.image_w[n]; d.img[n] = p.images[n];

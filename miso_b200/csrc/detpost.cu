@@ -134,8 +134,12 @@ __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev 
         const int g = n * S + c;
         const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
         const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        for (int q = tid; q < cnt; q += kDetFinalThreads)
-            if ((kb[q >> 6] >> (q & 63)) & 1ull) keys[atomicAdd(&s_cnt, 1)] = w.skey[st + q];
+        for (int q0 = 0; q0 < cnt; q0 += kDetFinalThreads) {
+            const int q = q0 + tid;
+            const bool kept = q < cnt && ((kb[q >> 6] >> (q & 63)) & 1ull);
+            const int slot = warp_alloc_slot(&s_cnt, kept);
+            if (kept) keys[slot] = w.skey[st + q];
+        }
     }
     __syncthreads();
     const int total = s_cnt;

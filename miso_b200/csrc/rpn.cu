@@ -160,13 +160,17 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
     unsigned long long* sel = w.sel + (size_t)n * Ktot + d.koff[l];
     unsigned long long* cand = w.cand + (size_t)n * sumA + d.aoff[l];
     const int end = min(d.AL[l], (chunk + 1) * kRpnChunk);
-    for (int m = chunk * kRpnChunk + tid; m < end; m += kRpnThreads) {
-        const unsigned int key = desc_score_key(__ldg(obj + m));
-        const int bin = (int)(key >> 20);
-        if (bin > tb) continue;
-        const unsigned long long ck = ((unsigned long long)key << 32) | (unsigned int)ref_index_from_mem(m, d.A[l], HW);
-        if (bin < tb) sel[atomicAdd(&w.n_sel[g], 1)] = ck;
-        else cand[atomicAdd(&w.n_cand[g], 1)] = ck;
+    for (int m0 = chunk * kRpnChunk; m0 < end; m0 += kRpnThreads) {   // warp-uniform trip count
+        const int m = m0 + tid;
+        unsigned int key = 0xffffffffu;
+        if (m < end) key = desc_score_key(__ldg(obj + m));
+        const int bin = (m < end) ? (int)(key >> 20) : kHistBins;
+        const unsigned long long ck =
+            ((unsigned long long)key << 32) | (unsigned int)(m < end ? ref_index_from_mem(m, d.A[l], HW) : 0);
+        const int s1 = warp_alloc_slot(&w.n_sel[g], bin < tb);
+        if (bin < tb) sel[s1] = ck;
+        const int s2 = warp_alloc_slot(&w.n_cand[g], bin == tb);
+        if (bin == tb) cand[s2] = ck;
     }
     __threadfence();
     __syncthreads();
@@ -298,11 +302,13 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
         const int g = n * d.L + l;
         const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
         const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        for (int q = tid; q < cnt; q += kRpnThreads) {
-            if ((kb[q >> 6] >> (q & 63)) & 1ull) {
+        for (int q0 = 0; q0 < cnt; q0 += kRpnThreads) {
+            const int q = q0 + tid;
+            const bool kept = q < cnt && ((kb[q >> 6] >> (q & 63)) & 1ull);
+            const int slot = warp_alloc_slot(&s_cnt, kept);
+            if (kept) {
                 const int p = st + q;
-                keys[atomicAdd(&s_cnt, 1)] =
-                    ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
+                keys[slot] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
             }
         }
     }

@@ -241,7 +241,7 @@ class CropOutput:
 
 
 def filter_and_crop(images: Sequence[Tensor], det_boxes: Tensor, det_scores: Tensor, det_counts: Tensor,
-                    threshold: float, capacity_bytes: Optional[int] = None) -> CropOutput:
+                    threshold: float, capacity_bytes: Optional[int] = None, boxes_are_xywh: bool = False) -> CropOutput:
     """images[n]: uint8 [H, W, C] or [H, W] on the device (the ORIGINAL image pixels, as
     skimage.io.imread returns them); det_* as produced by postprocess_detections."""
     lib = _lib.load()
@@ -262,6 +262,7 @@ def filter_and_crop(images: Sequence[Tensor], det_boxes: Tensor, det_scores: Ten
         p.image_h[i], p.image_w[i] = im.shape[0], im.shape[1]
         p.images[i] = im.data_ptr()
     p.threshold = float(threshold)
+    p.boxes_are_xywh = int(bool(boxes_are_xywh))
     dev = det_boxes.device
     b, s = _f32c(det_boxes), _f32c(det_scores)
     cnt = det_counts.to(torch.int32).contiguous()

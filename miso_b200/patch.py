@@ -1,0 +1,121 @@
+"""Drop-in wiring of the CUDA hot path into a loaded torchvision detection model
+and, optionally, into the torch dispatcher (b1).
+
+    model = torch.load("model.pt", weights_only=False).cuda().eval()
+    miso_b200.patch.patch_model(model)          # FasterRCNN or MaskRCNN instance
+    results = model(images)                     # same call, same return structure
+
+Patched points (inference only — `model.training` falls through to the original code, which
+needs autograd, the matcher and the samplers):
+    model.rpn.forward                       anchors + decode + filter_proposals      -> mb_rpn_proposals
+    model.roi_heads.box_roi_pool / mask_roi_pool   MultiScaleRoIAlign                -> mb_multiscale_roi_align
+    model.roi_heads.postprocess_detections  softmax/decode/clip/filters/NMS/top-k    -> mb_det_postprocess
+Hyper-parameters are read from the model instance at call time, never hard-coded.
+"""
+from __future__ import annotations
+
+import types
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import detection, ops
+from .detection import CPU_RULE_NUMEL, CUDA_RULE_NUMEL, DetConfig, RpnConfig
+
+_RULES = {"cpu": CPU_RULE_NUMEL, "cuda": CUDA_RULE_NUMEL, "vanilla": -1}
+
+
+def _rpn_forward(self, images, features: Dict[str, Tensor], targets=None):
+    """RegionProposalNetwork.forward (tv:models/detection/rpn.py:336-387), eval branch."""
+    if self.training:
+        return self._miso_b200_orig_forward(images, features, targets)
+    feats = list(features.values())
+    objectness, pred_bbox_deltas = self.head(feats)
+    cfg = RpnConfig.from_model(self, trick_numel=self._miso_b200_rule)
+    out = detection.rpn_proposals(objectness, pred_bbox_deltas, images.image_sizes, tuple(images.tensors.shape[-2:]), cfg)
+    boxes, _scores = out.as_lists()           # list per image, like the reference (one host sync)
+    return boxes, {}
+
+
+def _postprocess_detections(self, class_logits: Tensor, box_regression: Tensor, proposals: List[Tensor],
+                            image_shapes: List[Tuple[int, int]]):
+    """RoIHeads.postprocess_detections (tv:models/detection/roi_heads.py:680-737)."""
+    n = len(proposals)
+    counts = [int(p.shape[0]) for p in proposals]
+    r = max(max(counts), 1)
+    dev = class_logits.device
+    padded = torch.zeros((n, r, 4), dtype=torch.float32, device=dev)
+    for i, p in enumerate(proposals):
+        padded[i, : counts[i]] = p
+    cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
+    cfg = DetConfig.from_model(self, trick_numel=self._miso_b200_rule)
+    out = detection.postprocess_detections(class_logits, box_regression, padded, cnt, image_shapes, cfg, packed=True)
+    dc = out.counts.tolist()
+    boxes = [out.boxes_net[i, :c] for i, c in enumerate(dc)]
+    scores = [out.scores[i, :c] for i, c in enumerate(dc)]
+    labels = [out.labels[i, :c] for i, c in enumerate(dc)]
+    return boxes, scores, labels
+
+
+def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu"):
+    """Swap the post-head stages of a torchvision FasterRCNN / MaskRCNN instance for the CUDA
+    path. strategy_rule picks which of torchvision's batched_nms switch-over rules the fused
+    stages reproduce: "cpu" (numel > 4000, the reference CPU path = the parity oracle), "cuda"
+    (numel > 100000) or "vanilla" (always per-class). Returns the model."""
+    if getattr(model, "_miso_b200_patched", False):
+        return model
+    rule = _RULES[strategy_rule]
+    rpn, heads = model.rpn, model.roi_heads
+    rpn._miso_b200_orig_forward = rpn.forward
+    rpn._miso_b200_rule = rule
+    rpn.forward = types.MethodType(_rpn_forward, rpn)
+    heads._miso_b200_rule = rule
+    heads._miso_b200_orig_postprocess = heads.postprocess_detections
+    heads.postprocess_detections = types.MethodType(_postprocess_detections, heads)
+    heads._miso_b200_orig_box_roi_pool = heads.box_roi_pool
+    heads.box_roi_pool = ops.MultiScaleRoIAlign.from_torchvision(heads.box_roi_pool, exact=exact_roi_align)
+    if getattr(heads, "mask_roi_pool", None) is not None:
+        heads._miso_b200_orig_mask_roi_pool = heads.mask_roi_pool
+        heads.mask_roi_pool = ops.MultiScaleRoIAlign.from_torchvision(heads.mask_roi_pool, exact=exact_roi_align)
+    model._miso_b200_patched = True
+    return model
+
+
+def unpatch_model(model):
+    if not getattr(model, "_miso_b200_patched", False):
+        return model
+    model.rpn.forward = model.rpn._miso_b200_orig_forward
+    h = model.roi_heads
+    h.postprocess_detections = h._miso_b200_orig_postprocess
+    h.box_roi_pool = h._miso_b200_orig_box_roi_pool
+    if hasattr(h, "_miso_b200_orig_mask_roi_pool"):
+        h.mask_roi_pool = h._miso_b200_orig_mask_roi_pool
+    model._miso_b200_patched = False
+    return model
+
+
+_dispatch_lib: Optional["torch.library.Library"] = None
+
+
+def override_torchvision_ops() -> None:
+    """Operator-level drop-in: route torchvision::nms and torchvision::roi_align
+    for CUDA tensors through libmisob200, so unmodified callers (torchvision.ops.nms, batched_nms,
+    roi_align, MultiScaleRoIAlign) use it. Autograd / autocast / meta registrations are untouched;
+    only the CUDA forward kernels are replaced."""
+    global _dispatch_lib
+    if _dispatch_lib is not None:
+        return
+    import torchvision  # noqa: F401  (registers the op schemas)
+    lib = torch.library.Library("torchvision", "IMPL")
+
+    def nms_cuda(dets: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
+        return ops.nms(dets, scores, iou_threshold)
+
+    def roi_align_cuda(input: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int, pooled_width: int,
+                       sampling_ratio: int, aligned: bool) -> Tensor:
+        return ops.roi_align(input, rois, (int(pooled_height), int(pooled_width)), spatial_scale, sampling_ratio, aligned)
+
+    lib.impl("nms", nms_cuda, "CUDA", allow_override=True)
+    lib.impl("roi_align", roi_align_cuda, "CUDA", allow_override=True)
+    _dispatch_lib = lib

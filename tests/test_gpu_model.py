@@ -1,0 +1,174 @@
+"""Module-level drop-in and the kept entry points: a torchvision Faster R-CNN /
+Mask R-CNN with random-init weights is patched in place; every patched stage is compared with the
+UNPATCHED torchvision CPU code on the same stage inputs (captured from the GPU forward), and the
+`python -m miso.cli infer-object-detector-directory` command is run end to end."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import miso_path as M
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def make_model(kind="faster"):
+    from miso.object_detection.models import get_instance_segmentation_model, get_object_detection_model
+    torch.manual_seed(0)
+    m = get_object_detection_model(3) if kind == "faster" else get_instance_segmentation_model(3)
+    # sharpen the random heads so that scores spread over (0, 1) instead of sitting at 1/3
+    with torch.no_grad():
+        m.roi_heads.box_predictor.cls_score.weight.mul_(30.0)
+        m.rpn.head.cls_logits.weight.mul_(20.0)
+    return m.eval()
+
+
+def images(n=2, size=(512, 640), seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.rand(3, size[0] + 32 * i, size[1], generator=g) for i in range(n)]
+
+
+def match_rate(a, b, la, lb, tol=1e-3):
+    """fraction of boxes in a that have a same-label box in b within tol (relative to box scale)"""
+    if len(a) == 0:
+        return 1.0 if len(b) == 0 else 0.0
+    hit = 0
+    for i in range(len(a)):
+        d = np.abs(b - a[i]).max(axis=1) / max(np.abs(a[i]).max(), 1.0)
+        hit += bool(np.any((d < tol) & (lb == la[i])))
+    return hit / len(a)
+
+
+@pytest.mark.parametrize("kind", ["faster", "mask"])
+def test_patched_model_matches_reference_stage_by_stage(kind):
+    from miso_b200.patch import patch_model, unpatch_model
+    model = make_model(kind).to(DEV)
+    imgs = [im.to(DEV) for im in images()]
+    cap = {}
+
+    # capture the stage inputs of the GPU forward
+    def rpn_head_hook(mod, inp, out):
+        cap["objectness"], cap["deltas"] = [o.detach().cpu() for o in out[0]], [d.detach().cpu() for d in out[1]]
+    h1 = model.rpn.head.register_forward_hook(rpn_head_hook)
+    orig_pp = model.roi_heads.postprocess_detections
+
+    patch_model(model)
+    assert getattr(model, "_miso_b200_patched")
+    patched_pp = model.roi_heads.postprocess_detections
+
+    def spy_pp(class_logits, box_regression, proposals, image_shapes):
+        cap["logits"], cap["reg"] = class_logits.detach().cpu(), box_regression.detach().cpu()
+        cap["proposals"], cap["shapes"] = [p.detach().cpu() for p in proposals], list(image_shapes)
+        res = patched_pp(class_logits, box_regression, proposals, image_shapes)
+        cap["pp_out"] = [[t.detach().cpu() for t in r] for r in res]
+        return res
+    model.roi_heads.postprocess_detections = spy_pp
+    box_pool = model.roi_heads.box_roi_pool
+
+    def pool_hook(mod, inp, out):
+        cap["pool_in"] = ({k: v.detach().cpu() for k, v in inp[0].items()}, [b.detach().cpu() for b in inp[1]], list(inp[2]))
+        cap["pool_out"] = out.detach().cpu()
+    h2 = box_pool.register_forward_hook(pool_hook)
+    with torch.inference_mode():
+        out = model(imgs)
+    h1.remove(); h2.remove()
+    assert len(out) == len(imgs) and set(out[0]) >= {"boxes", "labels", "scores"}
+    if kind == "mask":
+        assert out[0]["masks"].shape[-2:] == imgs[0].shape[-2:]
+
+    # ---- reference CPU code on the captured inputs ----
+    cpu = make_model(kind)          # same seed -> same hyper-parameters (weights are irrelevant here)
+    from torchvision.models.detection.image_list import ImageList
+    from torchvision.models.detection.rpn import concat_box_prediction_layers
+    padded = (cap["objectness"][0].shape[-2] * 4, cap["objectness"][0].shape[-1] * 4)
+    il = ImageList(torch.zeros(len(imgs), 3, *padded), cap["shapes"])
+    with torch.inference_mode():
+        anchors = cpu.rpn.anchor_generator(il, cap["objectness"])
+        napl = [o.shape[1] * o.shape[2] * o.shape[3] for o in cap["objectness"]]
+        objectness, deltas = concat_box_prediction_layers(list(cap["objectness"]), list(cap["deltas"]))
+        decoded = cpu.rpn.box_coder.decode(deltas, anchors).view(len(imgs), -1, 4)
+        ref_props, _ = cpu.rpn.filter_proposals(decoded, objectness, il.image_sizes, napl)
+    for p_gpu, p_ref in zip(cap["proposals"], ref_props):
+        assert p_gpu.shape == p_ref.shape
+        assert cases.box_rel_err(p_gpu.numpy(), p_ref.numpy()) < 1e-5
+    # RoIAlign: bit-exact against torchvision's CPU pooler on identical inputs
+    with torch.inference_mode():
+        ref_pool = cpu.roi_heads.box_roi_pool(cap["pool_in"][0], cap["pool_in"][1], cap["pool_in"][2])
+    assert torch.equal(cap["pool_out"], ref_pool)
+    # detection post-processing on identical inputs
+    with torch.inference_mode():
+        rb, rs, rl = cpu.roi_heads.postprocess_detections(cap["logits"], cap["reg"], cap["proposals"], cap["shapes"])
+    for i in range(len(imgs)):
+        gb, gs, gl = cap["pp_out"][0][i], cap["pp_out"][1][i], cap["pp_out"][2][i]
+        assert torch.equal(gl, rl[i])
+        assert cases.box_rel_err(gb.numpy(), rb[i].numpy()) < 1e-5
+        assert float((gs - rs[i]).abs().max()) < 1e-6 if len(gs) else True
+
+    # ---- whole model: patched vs unpatched torchvision CUDA path ----
+    model.roi_heads.postprocess_detections = patched_pp
+    with torch.inference_mode():
+        a = model(imgs)
+        unpatch_model(model)
+        assert model.roi_heads.postprocess_detections == orig_pp
+        b = model(imgs)
+    for x, y in zip(a, b):
+        r = match_rate(x["boxes"].cpu().numpy(), y["boxes"].cpu().numpy(), x["labels"].cpu().numpy(), y["labels"].cpu().numpy())
+        assert r > 0.9, r
+
+
+def test_dispatcher_override_routes_torchvision_ops():
+    import torchvision
+    from miso_b200.patch import override_torchvision_ops
+    from oracle import native
+    rng = np.random.default_rng(1)
+    b, s = cases.random_boxes(rng, 800), cases.distinct_scores(rng, 800)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        override_torchvision_ops()
+    keep = torchvision.ops.nms(torch.from_numpy(b).to(DEV), torch.from_numpy(s).to(DEV), 0.5)
+    assert np.array_equal(keep.cpu().numpy(), native.nms(b, s, 0.5))
+    x = torch.randn(1, 8, 30, 30, device=DEV)
+    rois = torch.tensor([[0, 2.5, 3.5, 20.0, 25.0]], device=DEV)
+    out = torchvision.ops.roi_align(x, rois, 7, 1.0, 2)
+    assert np.array_equal(out.cpu().numpy(), native.roi_align(x.cpu().numpy(), rois.cpu().numpy(), 1.0, 7, 7, 2, False))
+
+
+def test_cli_infer_directory_writes_reference_crops(tmp_path):
+    from click.testing import CliRunner
+    from PIL import Image
+    import miso.cli as cli
+    model = make_model("faster")
+    mdir = tmp_path / "models" / "m1"
+    mdir.mkdir(parents=True)
+    torch.save(model, mdir / "model.pt")                    # whole pickled module, like the reference
+    (mdir / "labels.txt").write_text("0,Coccolith\n1,Coccosphere\n")
+    idir = tmp_path / "in" / "sub"
+    idir.mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    arrs = {}
+    for name in ("a.png", "b.png"):
+        arr = rng.integers(0, 256, (384, 512, 3), dtype=np.uint8)
+        Image.fromarray(arr).save(idir / name)
+        arrs[name] = arr
+    odir = tmp_path / "out"
+    res = CliRunner().invoke(cli.cli, ["infer-object-detector-directory", "-i", str(tmp_path / "in"), "-o", str(odir),
+                                       "--model-dir", str(tmp_path / "models"), "--model", "m1", "--threshold", "0.3",
+                                       "--batch-size", "2"], catch_exceptions=False)
+    assert res.exit_code == 0, res.output
+    files = sorted(p for p in odir.rglob("*.png"))
+    assert files, "no crops written"
+    for f in files:
+        assert f.parent.name in ("Coccolith", "Coccosphere") and f.parent.parent.name == "sub"
+        stem, x, y, w, h = f.stem.rsplit("_", 4)
+        crop = np.asarray(Image.open(f))
+        src = arrs[stem + ".png"]
+        assert crop.shape[0] <= src.shape[0] and crop.shape[1] <= src.shape[1] and crop.ndim == 3
+        # the file name carries the rounded bounds; the pixels must be a slice of the source image there
+        xs, ys = int(x), int(y)
+        found = any(np.array_equal(crop, src[yy:yy + crop.shape[0], xx:xx + crop.shape[1]])
+                    for yy in range(max(ys - 1, 0), ys + 2) for xx in range(max(xs - 1, 0), xs + 2))
+        assert found

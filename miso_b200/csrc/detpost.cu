@@ -21,6 +21,7 @@ namespace mb {
 constexpr int kDetThreads = 256;
 constexpr int kDetFinalThreads = 1024;
 constexpr int kDetSortCap = 16384;
+constexpr int kDetMergeMaxRuns = 8;
 
 struct DetDev {
     int N, C, max_props, dpi;
@@ -123,29 +124,71 @@ __global__ void k_det_seg_starts(int G, int max_props, int* seg_start) {
 __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev d, const DetImages im, DetScratch w,
                                                                   float4* det_boxes, float4* det_boxes_net,
                                                                   float* det_scores, long long* det_labels,
-                                                                  int* det_counts) {
+                                                                  int* det_counts, int use_merge) {
     extern __shared__ unsigned long long keys[];
     __shared__ int s_cnt;
+    __shared__ int run_off[kDetMergeMaxRuns + 1];
+    __shared__ int wpre[kDetMergeMaxRuns][kSweepSmallMaxWords + 1];
     const int n = blockIdx.x, tid = threadIdx.x;
     const int S = d.C - 1, F = d.max_props * S;
-    if (tid == 0) s_cnt = 0;
-    __syncthreads();
-    for (int c = 0; c < S; ++c) {
-        const int g = n * S + c;
-        const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
-        const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        for (int q0 = 0; q0 < cnt; q0 += kDetFinalThreads) {
-            const int q = q0 + tid;
-            const bool kept = q < cnt && ((kb[q >> 6] >> (q & 63)) & 1ull);
-            const int slot = warp_alloc_slot(&s_cnt, kept);
-            if (kept) keys[slot] = w.skey[st + q];
+    int total;
+    if (use_merge) {
+        // few classes: every class's kept list is already sorted, so merge by rank (no sort);
+        // the merged order lands in keys[total .. 2*total)
+        if (tid < S) {
+            const int g = n * S + tid;
+            const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
+            const int T = w.seg.seg_words[g];
+            int acc = 0;
+            for (int q = 0; q < T; ++q) { wpre[tid][q] = acc; acc += __popcll(kb[q]); }
+            wpre[tid][T] = acc;
         }
+        __syncthreads();
+        if (tid == 0) {
+            int acc = 0;
+            for (int c = 0; c < S; ++c) { run_off[c] = acc; acc += wpre[c][w.seg.seg_words[n * S + c]]; }
+            run_off[S] = acc;
+        }
+        __syncthreads();
+        total = run_off[S];
+        for (int c = 0; c < S; ++c) {
+            const int g = n * S + c;
+            const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
+            const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
+            for (int q = tid; q < cnt; q += kDetFinalThreads) {
+                const unsigned long long word = kb[q >> 6];
+                if ((word >> (q & 63)) & 1ull)
+                    keys[total + run_off[c] + wpre[c][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull))] = w.skey[st + q];
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < total; e += kDetFinalThreads) {
+            int c = 0;
+            while (e >= run_off[c + 1]) ++c;
+            const int rank = merged_rank(keys + total, run_off, S, c, e - run_off[c]);
+            keys[rank] = keys[total + e];
+        }
+        __syncthreads();
+    } else {
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int c = 0; c < S; ++c) {
+            const int g = n * S + c;
+            const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
+            const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
+            for (int q0 = 0; q0 < cnt; q0 += kDetFinalThreads) {
+                const int q = q0 + tid;
+                const bool kept = q < cnt && ((kb[q >> 6] >> (q & 63)) & 1ull);
+                const int slot = warp_alloc_slot(&s_cnt, kept);
+                if (kept) keys[slot] = w.skey[st + q];
+            }
+        }
+        __syncthreads();
+        total = s_cnt;
+        const int np2 = next_pow2(max(total, 2));
+        for (int i = total + tid; i < np2; i += kDetFinalThreads) keys[i] = ~0ull;
+        bitonic_sort_smem(keys, np2);
     }
-    __syncthreads();
-    const int total = s_cnt;
-    const int np2 = next_pow2(max(total, 2));
-    for (int i = total + tid; i < np2; i += kDetFinalThreads) keys[i] = ~0ull;
-    bitonic_sort_smem(keys, np2);
     const int nout = min(total, d.dpi);
     for (int i = tid; i < d.dpi; i += kDetFinalThreads) {
         float4 b = make_float4(0, 0, 0, 0);
@@ -232,11 +275,13 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     rc = launch_mask_and_sweep(w.sbox, w.seg, G, d.max_props, p->nms_thresh, w.mask, w.keepbits, d.dpi, stream, w.seg_offset);
     if (rc != MB_OK) return rc;
     const long long per_seg = d.max_props < d.dpi ? d.max_props : d.dpi;
-    const int cap = next_pow2((int)((d.C - 1) * per_seg) > 2 ? (int)((d.C - 1) * per_seg) : 2);
-    const int smem = cap * (int)sizeof(unsigned long long);
+    const int bound = (int)((d.C - 1) * per_seg);
+    const int use_merge = (d.C - 1) <= kDetMergeMaxRuns && d.max_props <= 64 * kSweepSmallMaxWords && 2 * bound <= kDetSortCap;
+    const int cap = use_merge ? 2 * bound : next_pow2(bound > 2 ? bound : 2);   // merge keeps source + merged order
+    const int smem = (cap > 2 ? cap : 2) * (int)sizeof(unsigned long long);
     MB_CUDA(cudaFuncSetAttribute(k_det_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k_det_finalize<<<d.N, kDetFinalThreads, smem, stream>>>(d, im, w, (float4*)det_boxes, (float4*)det_boxes_net, det_scores,
-                                                           (long long*)det_labels, det_counts);
+                                                           (long long*)det_labels, det_counts, use_merge);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

@@ -334,12 +334,33 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_staged(const mb_ro
 constexpr int kMaxGroups = 32;
 
 template <bool EXACT>
+__device__ __forceinline__ float bin_value(const float* sp, const int4* __restrict__ toff, const float4* __restrict__ tw) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int4 o = toff[smp];
+        const float4 wv = tw[smp];
+        const float v1 = sp[o.x], v2 = sp[o.y], v3 = sp[o.z], v4 = sp[o.w];
+        if (EXACT) {   // ((w1*v1 + w2*v2) + w3*v3) + w4*v4, then acc + that: the reference's order
+            float t = __fmul_rn(wv.x, v1);
+            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
+            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
+            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
+            acc = __fadd_rn(acc, t);
+        } else {
+            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
+        }
+    }
+    return __fmul_rn(acc, 0.25f);   // acc / 4: exact scaling
+}
+
+template <bool EXACT>
 __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_align_params p,
                                                                 const float* __restrict__ rois,
                                                                 float* __restrict__ out, int* __restrict__ levels_out,
                                                                 int patch_floats) {
     extern __shared__ __align__(16) float smem[];
-    __shared__ Tap ytab[kMaxSamples], xtab[kMaxSamples];
+    __shared__ Tap ytab[32], xtab[32];
     __shared__ int grp_ph0[kMaxGroups + 1], grp_y0[kMaxGroups], grp_rows[kMaxGroups], grp_direct[kMaxGroups];
     __shared__ int s_ngroups;
 
@@ -363,6 +384,10 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
     __syncthreads();
 
     const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
+    const size_t plane = (size_t)g.H * g.W;
+    const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
+    // 16-byte vector staging needs every footprint row to start on a float4 boundary
+    const bool vec4 = ((g.W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
     int x0 = 0, x1 = -1;
     {
         int i = 0;
@@ -371,8 +396,9 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
         while (j >= 0 && !xtab[j].valid) --j;
         if (i <= j) { x0 = xtab[i].lo; x1 = xtab[j].hi; }
     }
-    const int cols = x1 - x0 + 1;
     const bool empty = bad_batch || x1 < 0;
+    if (vec4 && !empty) { x0 &= ~3; x1 |= 3; }   // W % 4 == 0, so x1 | 3 <= W - 1
+    const int cols = x1 - x0 + 1;
 
     // ---- footprint groups: maximal runs of output rows whose rows x cols fit the staging buffer ----
     if (tid == 0) {
@@ -422,8 +448,6 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
     }
     __syncthreads();
 
-    const size_t plane = (size_t)g.H * g.W;
-    const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
     const int nchunks = (p.channels + kChunk - 1) / kChunk;
     float* dst_roi = out + (size_t)k * p.channels * nbins;
 
@@ -440,57 +464,72 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
             const bool direct = grp_direct[gi] != 0;
             const int P = rows * cols;
             const int pitch = P + ((33 - (P & 31)) & 31);
-            // ---- stage: thread = footprint pixel (x fastest => coalesced rows), loop over channels ----
             if (!direct && P > 0) {
-                const int NG = P <= kRoiThreads ? kRoiThreads / P : 1;   // channel groups running in parallel
-                for (int pos0 = 0; pos0 < P; pos0 += kRoiThreads) {
-                    int pos = pos0 + tid, grp = 0;
-                    if (NG > 1) { grp = tid / P; pos = tid - grp * P; }
-                    if (pos < P && grp < NG) {
-                        const int rr = pos / cols, x = pos - rr * cols;
-                        const float* src = base + (size_t)grp * plane + (size_t)(gy0 + rr) * g.W + x0 + x;
-                        float* dp = patch + grp * pitch + pos;
-                        const size_t sstep = (size_t)NG * plane;
-                        const int dstep = NG * pitch;
-                        int cc = grp;
-                        for (; cc + 7 * NG < nch; cc += 8 * NG) {
-                            float v[8];
+                if (vec4) {
+                    // ---- stage, 16-byte loads: lane = (channel c%4, float4 slot). A warp instruction
+                    //      reads 4 channels x 128 contiguous bytes; the four scalar stores of a float4
+                    //      land on 32 distinct banks because the plane pitch is 1 (mod 32). ----
+                    const int c4 = cols >> 2, P4 = rows * c4;
+                    const int csub = tid & 3;
+                    for (int pos4 = tid >> 2; pos4 < P4; pos4 += kRoiThreads / 4) {
+                        const int rr = pos4 / c4, x4 = pos4 - rr * c4;
+                        const float4* src = reinterpret_cast<const float4*>(
+                            base + (size_t)csub * plane + (size_t)(gy0 + rr) * g.W + x0 + 4 * x4);
+                        float* dp = patch + csub * pitch + 4 * pos4;
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u * sstep);
+                        for (int half = 0; half < 2; ++half) {      // 2 x 4 loads of 16 bytes in flight
+                            float4 v[4];
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) dp[u * dstep] = v[u];
-                            src += 8 * sstep; dp += 8 * dstep;
+                            for (int u = 0; u < 4; ++u)
+                                if ((half * 4 + u) * 4 + csub < nch) v[u] = __ldg(src + (size_t)(half * 4 + u) * plane);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if ((half * 4 + u) * 4 + csub < nch) {
+                                    float* d = dp + (half * 4 + u) * 4 * pitch;
+                                    d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+                                }
                         }
-                        for (; cc < nch; cc += NG) { *dp = __ldg(src); src += sstep; dp += dstep; }
+                    }
+                } else {
+                    // ---- stage, scalar: thread = footprint pixel (x fastest), loop over channels ----
+                    const int NG = P <= kRoiThreads ? kRoiThreads / P : 1;
+                    for (int pos0 = 0; pos0 < P; pos0 += kRoiThreads) {
+                        int pos = pos0 + tid, grp = 0;
+                        if (NG > 1) { grp = tid / P; pos = tid - grp * P; }
+                        if (pos < P && grp < NG) {
+                            const int rr = pos / cols, x = pos - rr * cols;
+                            const float* src = base + (size_t)grp * plane + (size_t)(gy0 + rr) * g.W + x0 + x;
+                            float* dp = patch + grp * pitch + pos;
+                            const size_t sstep = (size_t)NG * plane;
+                            const int dstep = NG * pitch;
+                            int cc = grp;
+                            for (; cc + 7 * NG < nch; cc += 8 * NG) {
+                                float v[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u * sstep);
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) dp[u * dstep] = v[u];
+                                src += 8 * sstep; dp += 8 * dstep;
+                            }
+                            for (; cc < nch; cc += NG) { *dp = __ldg(src); src += sstep; dp += dstep; }
+                        }
                     }
                 }
             }
             __syncthreads();
             // ---- bins of this group: warp per bin, lane per channel ----
             const int b0 = grp_ph0[gi] * PW, b1 = grp_ph0[gi + 1] * PW;
-            const float* sp = direct ? (base + (size_t)lane * plane) : (patch + lane * pitch);
-            if (!direct && P == 0) {            // no valid sample row in this group: zeros (nothing was staged)
+            if (direct) {
+                const float* gp = base + (size_t)lane * plane;            // global gathers (rare)
+                if (lane < nch)
+                    for (int b = b0 + warp; b < b1; b += kRoiWarps)
+                        out_s[lane * opitch + b] = bin_value<EXACT>(gp, tab_off + b * 4, tab_w + b * 4);
+            } else if (P == 0) {              // no valid sample row in this group: zeros (nothing was staged)
                 for (int b = b0 + warp; b < b1; b += kRoiWarps) out_s[lane * opitch + b] = 0.0f;
             } else if (lane < nch) {
-                for (int b = b0 + warp; b < b1; b += kRoiWarps) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int smp = 0; smp < 4; ++smp) {
-                        const int4 o = tab_off[b * 4 + smp];
-                        const float4 wv = tab_w[b * 4 + smp];
-                        const float v1 = sp[o.x], v2 = sp[o.y], v3 = sp[o.z], v4 = sp[o.w];
-                        if (EXACT) {
-                            float t = __fmul_rn(wv.x, v1);
-                            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
-                            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
-                            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
-                            acc = __fadd_rn(acc, t);
-                        } else {
-                            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
-                        }
-                    }
-                    out_s[lane * opitch + b] = __fmul_rn(acc, 0.25f);   // acc / 4: exact scaling
-                }
+                const float* sp = patch + lane * pitch;                   // shared memory: LDS, 32-bit addresses
+                for (int b = b0 + warp; b < b1; b += kRoiWarps)
+                    out_s[lane * opitch + b] = bin_value<EXACT>(sp, tab_off + b * 4, tab_w + b * 4);
             }
             __syncthreads();
         }
@@ -569,7 +608,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     const bool staged = p.sampling_ratio > 0 && p.sampling_ratio * p.pooled_h <= kMaxSamples &&
                         p.sampling_ratio * p.pooled_w <= kMaxSamples && nbins <= 512 &&
                         num_rois * chunks < (1ll << 31);
-    if (staged && p.sampling_ratio == 2 && nbins <= 256 && num_rois < (1ll << 31)) {
+    if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;

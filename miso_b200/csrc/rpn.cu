@@ -178,20 +178,16 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // ---- last CTA: resolve the threshold bin, then sort the k winners ----
+    // ---- last CTA: resolve the threshold bin, then sort exactly k winners ----
     const int k = d.k[l];
     const int na = w.n_above[g];
     const int nc = __ldcg(&w.n_cand[g]);
     int need = k - na;  // winners still to take from the candidates (1 <= need <= nc)
-    int total;
-    if (na + nc <= kSelectSortCap) {
-        for (int i = tid; i < na; i += kRpnThreads) keys[i] = __ldcg(&sel[i]);
-        for (int i = tid; i < nc; i += kRpnThreads) keys[na + i] = __ldcg(&cand[i]);
-        total = na + nc;
-    } else {
-        // Too many ties in the threshold bin for one shared-memory sort: radix-select the
-        // need-th smallest candidate key over the remaining 52 bits, 8 bits per pass.
-        unsigned long long prefix = 0, pmask = 0;
+    unsigned long long prefix = 0x000fffffffffffffull;   // take every candidate unless narrowed below
+    if (nc > need) {
+        // radix-select the need-th smallest candidate key over the remaining 52 bits, 8 bits per pass
+        unsigned long long pmask = 0;
+        prefix = 0;
         for (int shift = 44; shift >= -4; shift -= 8) {
             const int sft = shift < 0 ? 0 : shift;
             const int bits = shift < 0 ? 4 : 8;
@@ -202,11 +198,22 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
                 if ((ck & pmask) == prefix) atomicAdd(&hist256[(int)((ck >> sft) & ((1u << bits) - 1))], 1);
             }
             __syncthreads();
-            if (tid == 0) {
-                int cum = 0, dgt = 0;
-                for (; dgt < (1 << bits); ++dgt) { if (cum + hist256[dgt] >= need) break; cum += hist256[dgt]; }
-                s_need = need - cum;
-                s_thr = prefix | ((unsigned long long)dgt << sft);
+            if (tid < 32) {   // warp scan over 256 bins, 8 per lane
+                int loc[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { loc[q] = hist256[tid * 8 + q]; sum += loc[q]; }
+                int inc = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, inc, o); if (tid >= o) inc += y; }
+                int cum = inc - sum;   // candidates in bins below this lane's first bin
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (cum < need && cum + loc[q] >= need) {
+                        s_need = need - cum;
+                        s_thr = prefix | ((unsigned long long)(tid * 8 + q) << sft);
+                    }
+                    cum += loc[q];
+                }
             }
             __syncthreads();
             need = s_need;
@@ -215,16 +222,20 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
             __syncthreads();
         }
         // prefix is now the exact low-52-bit value of the last winner (keys are unique)
-        if (tid == 0) s_prefix_ok = 0;
-        __syncthreads();
-        for (int i = tid; i < na; i += kRpnThreads) keys[i] = __ldcg(&sel[i]);
-        for (int i = tid; i < nc; i += kRpnThreads) {
-            const unsigned long long ck = __ldcg(&cand[i]);
-            if ((ck & 0x000fffffffffffffull) <= prefix) keys[na + atomicAdd(&s_prefix_ok, 1)] = ck;
-        }
-        __syncthreads();
-        total = na + s_prefix_ok;  // == k
     }
+    if (tid == 0) s_prefix_ok = 0;
+    __syncthreads();
+    for (int i = tid; i < na; i += kRpnThreads) keys[i] = __ldcg(&sel[i]);
+    for (int i0 = 0; i0 < nc; i0 += kRpnThreads) {
+        const int i = i0 + tid;
+        unsigned long long ck = 0;
+        bool win = false;
+        if (i < nc) { ck = __ldcg(&cand[i]); win = (ck & 0x000fffffffffffffull) <= prefix; }
+        const int slot = warp_alloc_slot(&s_prefix_ok, win);
+        if (win) keys[na + slot] = ck;
+    }
+    __syncthreads();
+    const int total = na + s_prefix_ok;  // == k
     const int np2 = next_pow2(max(total, 2));
     for (int i = total + tid; i < np2; i += kRpnThreads) keys[i] = ~0ull;
     bitonic_sort_smem(keys, np2);
@@ -289,45 +300,61 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_decode(const RpnDev d, cons
     if (tid == 0) { w.seg.seg_start[g] = seg_start; w.seg.seg_count[g] = s_base; }
 }
 
-// one CTA per image: order the kept boxes of all levels by (score desc, candidate order asc)
+// one CTA per image: merge the kept boxes of all levels by (score desc, candidate order asc).
+// Every level's kept list is already in that order (sweep order), so the global rank of a box is
+// its index in its own list plus, per other level, a binary search — no sort.
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, RpnScratch w, float4* proposals_out,
                                                              float* scores_out, int* counts_out, int sort_cap) {
     extern __shared__ unsigned long long keys[];
-    __shared__ int s_cnt;
+    __shared__ int run_off[MB_MAX_LEVELS + 1];
+    __shared__ int wpre[MB_MAX_LEVELS][kSweepSmallMaxWords + 1];
     const int n = blockIdx.x, tid = threadIdx.x;
     const int Ktot = d.koff[d.L];
-    if (tid == 0) s_cnt = 0;
+    // per level: exclusive popcount prefix over the keep words, and the run offsets
+    if (tid < d.L) {
+        const int g = n * d.L + tid;
+        const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
+        const int T = w.seg.seg_words[g];
+        int acc = 0;
+        for (int q = 0; q < T; ++q) { wpre[tid][q] = acc; acc += __popcll(kb[q]); }
+        wpre[tid][T] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int l = 0; l < d.L; ++l) { run_off[l] = acc; acc += wpre[l][w.seg.seg_words[n * d.L + l]]; }
+        run_off[d.L] = acc;
+    }
     __syncthreads();
     for (int l = 0; l < d.L; ++l) {
         const int g = n * d.L + l;
         const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
         const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        for (int q0 = 0; q0 < cnt; q0 += kRpnThreads) {
-            const int q = q0 + tid;
-            const bool kept = q < cnt && ((kb[q >> 6] >> (q & 63)) & 1ull);
-            const int slot = warp_alloc_slot(&s_cnt, kept);
-            if (kept) {
+        for (int q = tid; q < cnt; q += kRpnThreads) {
+            const unsigned long long word = kb[q >> 6];
+            if ((word >> (q & 63)) & 1ull) {
+                const int j = wpre[l][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull));
                 const int p = st + q;
-                keys[slot] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
+                keys[run_off[l] + j] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
             }
         }
     }
     __syncthreads();
-    const int total = s_cnt;
-    const int np2 = next_pow2(max(total, 2));
-    for (int i = total + tid; i < np2; i += kRpnThreads) keys[i] = ~0ull;
-    bitonic_sort_smem(keys, np2);
+    const int total = run_off[d.L];
     const int nout = min(total, d.post_nms_top_n);
-    for (int i = tid; i < d.post_nms_top_n; i += kRpnThreads) {
-        float4 b = make_float4(0, 0, 0, 0);
-        float s = 0.0f;
-        if (i < nout) {
-            const int p = n * Ktot + (int)(keys[i] & 0xffffffffull);
-            b = w.rbox[p];
-            s = w.score[p];
+    for (int e = tid; e < total; e += kRpnThreads) {
+        int l = 0;
+        while (e >= run_off[l + 1]) ++l;
+        const int rank = merged_rank(keys, run_off, d.L, l, e - run_off[l]);
+        if (rank < nout) {
+            const int p = n * Ktot + (int)(keys[e] & 0xffffffffull);
+            proposals_out[(size_t)n * d.post_nms_top_n + rank] = w.rbox[p];
+            scores_out[(size_t)n * d.post_nms_top_n + rank] = w.score[p];
         }
-        proposals_out[(size_t)n * d.post_nms_top_n + i] = b;
-        scores_out[(size_t)n * d.post_nms_top_n + i] = s;
+    }
+    for (int i = nout + tid; i < d.post_nms_top_n; i += kRpnThreads) {
+        proposals_out[(size_t)n * d.post_nms_top_n + i] = make_float4(0, 0, 0, 0);
+        scores_out[(size_t)n * d.post_nms_top_n + i] = 0.0f;
     }
     if (tid == 0) counts_out[n] = nout;
     (void)sort_cap;

@@ -29,4 +29,25 @@ __device__ inline void bitonic_sort_smem(unsigned long long* a, int n) {
     __syncthreads();
 }
 
+// Number of keys < key in the ascending run a[0..n) (keys are unique).
+__device__ __forceinline__ int lower_bound_smem(const unsigned long long* a, int n, unsigned long long key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Rank of element j of run s in the merge of S ascending runs stored back to back in `keys`
+// (run r occupies [off[r], off[r+1])): its own index plus, for every other run, the number of
+// keys below it. Replaces a full sort when the inputs are already sorted per run.
+__device__ __forceinline__ int merged_rank(const unsigned long long* keys, const int* off, int S, int s, int j) {
+    const unsigned long long key = keys[off[s] + j];
+    int rank = j;
+    for (int r = 0; r < S; ++r)
+        if (r != s) rank += lower_bound_smem(keys + off[r], off[r + 1] - off[r], key);
+    return rank;
+}
+
 }  // namespace mb

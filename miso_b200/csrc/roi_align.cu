@@ -18,6 +18,8 @@
 //   footprint whose single output row does not fit falls back to direct global gathers.
 // Direct kernel (sampling_ratio <= 0 or very large bins): one thread per output element.
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -549,6 +551,266 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Pipelined variant of the sampling_ratio == 2 kernel: the CTA is split into 4 producer warps
+// and 8 consumer warps that hand footprints over through a 2-stage shared-memory ring guarded
+// by mbarriers (full/empty per stage). Producers only stage (global -> registers -> smem) and
+// absorb the global-load latency; consumers only read shared memory (bins) and write results,
+// so neither side ever waits at a CTA-wide barrier for the other's phase.
+// ------------------------------------------------------------------------------------------
+constexpr int kPipeConsumers = 256, kPipeProducers = 128, kPipeThreads = kPipeConsumers + kPipeProducers;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    const unsigned addr = smem_u32(bar);
+    int spins = 0;
+    while (true) {
+        unsigned done;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        if (++spins > (1 << 26)) __trap();   // a protocol bug must fault, never hang the GPU
+    }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float bin_value_smem(unsigned sbase, const int4* __restrict__ toff, const float4* __restrict__ tw) {
+    // toff holds BYTE offsets; sbase is the lane's 32-bit shared address: one add per tap
+    float acc = 0.0f;
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int4 o = toff[smp];
+        const float4 wv = tw[smp];
+        float v1, v2, v3, v4;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(sbase + o.x));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(sbase + o.y));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(sbase + o.z));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4) : "r"(sbase + o.w));
+        if (EXACT) {
+            float t = __fmul_rn(wv.x, v1);
+            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
+            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
+            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
+            acc = __fadd_rn(acc, t);
+        } else {
+            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
+        }
+    }
+    return __fmul_rn(acc, 0.25f);
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kPipeThreads, 2) k_roi_align_sr2_pipe(const mb_roi_align_params p,
+                                                                      const float* __restrict__ rois,
+                                                                      float* __restrict__ out, int* __restrict__ levels_out,
+                                                                      int patch_floats) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ Tap ytab[32], xtab[32];
+    __shared__ int grp_ph0[kMaxGroups + 1], grp_y0[kMaxGroups], grp_rows[kMaxGroups], grp_direct[kMaxGroups];
+    __shared__ int s_ngroups;
+    __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2];
+
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
+    const int opitch = (nbins & 1) ? nbins : nbins + 1;
+    const int obuf = (kChunk * opitch + 3) & ~3;            // floats per output buffer, 16-byte multiple
+    float* out_s = smem;                                    // [2][kChunk][opitch]
+    float* patch = out_s + 2 * obuf;                        // [2][patch_floats]
+    int4* tab_off = reinterpret_cast<int4*>(patch + 2 * patch_floats);   // [nbins][4], byte offsets
+    float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);      // [nbins][4]
+
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);
+    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
+    const int ny = PH * 2, nx = PW * 2;
+    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
+    if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
+    if (tid == 128) { mbar_init(&bar_full[0], kPipeProducers); mbar_init(&bar_full[1], kPipeProducers);
+                      mbar_init(&bar_empty[0], kPipeConsumers); mbar_init(&bar_empty[1], kPipeConsumers); }
+    __syncthreads();
+
+    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
+    const size_t plane = (size_t)g.H * g.W;
+    const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
+    const bool vec4 = ((g.W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
+    int x0 = 0, x1 = -1;
+    {
+        int i = 0;
+        while (i < nx && !xtab[i].valid) ++i;
+        int j = nx - 1;
+        while (j >= 0 && !xtab[j].valid) --j;
+        if (i <= j) { x0 = xtab[i].lo; x1 = xtab[j].hi; }
+    }
+    const bool empty = bad_batch || x1 < 0;
+    const int nchunks = (p.channels + kChunk - 1) / kChunk;
+    float* dst_roi = out + (size_t)k * p.channels * nbins;
+    if (empty) {   // dead row / nothing to sample: zeros, no pipeline
+        const long long total = (long long)p.channels * nbins;
+        for (long long i = tid; i < total; i += kPipeThreads) dst_roi[i] = 0.0f;
+        return;
+    }
+    if (vec4) { x0 &= ~3; x1 |= 3; }
+    const int cols = x1 - x0 + 1;
+
+    if (tid == 0) {
+        int ng = 0, ph0 = 0;
+        while (ph0 < PH) {
+            int gy0 = 0x7fffffff, gy1 = -1, ph1 = ph0;
+            while (ph1 < PH) {
+                int ny0 = gy0, ny1 = gy1;
+                for (int i = ph1 * 2; i < ph1 * 2 + 2; ++i)
+                    if (ytab[i].valid) { ny0 = min(ny0, ytab[i].lo); ny1 = max(ny1, ytab[i].hi); }
+                const int pix = (ny1 >= 0 ? ny1 - ny0 + 1 : 0) * cols;
+                if ((pix + ((33 - (pix & 31)) & 31)) * kChunk > patch_floats) break;
+                gy0 = ny0; gy1 = ny1; ++ph1;
+            }
+            const bool direct = (ph1 == ph0);
+            if (direct) {
+                ph1 = ph0 + 1;
+                for (int i = ph0 * 2; i < ph0 * 2 + 2; ++i)
+                    if (ytab[i].valid) { gy0 = min(gy0, ytab[i].lo); gy1 = max(gy1, ytab[i].hi); }
+            }
+            grp_ph0[ng] = ph0; grp_y0[ng] = gy1 >= 0 ? gy0 : 0; grp_rows[ng] = gy1 >= 0 ? gy1 - gy0 + 1 : 0;
+            grp_direct[ng] = direct;
+            ++ng; ph0 = ph1;
+        }
+        grp_ph0[ng] = PH;
+        s_ngroups = ng;
+    }
+    __syncthreads();
+    const int ngroups = s_ngroups;
+
+    for (int e = tid; e < nbins * 4; e += kPipeThreads) {
+        const int b = e >> 2, smp = e & 3;
+        const int ph = b / PW, pw = b - ph * PW;
+        int gi = 0;
+        while (gi + 1 < ngroups && ph >= grp_ph0[gi + 1]) ++gi;
+        const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
+        const bool ok = Y.valid && X.valid;
+        const bool direct = grp_direct[gi] != 0;
+        const int rs = direct ? g.W : cols;
+        const int oy = direct ? 0 : grp_y0[gi], ox = direct ? 0 : x0;
+        const int ylo = ok ? (Y.lo - oy) * rs : 0, yhi = ok ? (Y.hi - oy) * rs : 0;
+        const int xlo = ok ? X.lo - ox : 0, xhi = ok ? X.hi - ox : 0;
+        tab_off[e] = make_int4(4 * (ylo + xlo), 4 * (ylo + xhi), 4 * (yhi + xlo), 4 * (yhi + xhi));   // bytes
+        tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    const int nunits = nchunks * ngroups;
+    if (warp >= kPipeConsumers / 32) {
+        // =============================== PRODUCERS ===============================
+        const int ptid = tid - kPipeConsumers;
+        for (int u = 0; u < nunits; ++u) {
+            const int chunk = u / ngroups, gi = u - chunk * ngroups;
+            const int st = u & 1;
+            mbar_wait(&bar_empty[st], ((u >> 1) & 1) ^ 1);          // slot free (passes immediately the first time)
+            const int rows = grp_rows[gi], gy0 = grp_y0[gi];
+            const int P = rows * cols;
+            const int pitch = P + ((33 - (P & 31)) & 31);
+            const int c0 = chunk * kChunk;
+            const int nch = min(kChunk, p.channels - c0);
+            const float* base = feat + (size_t)c0 * plane;
+            float* pbuf = patch + st * patch_floats;
+            if (!grp_direct[gi] && P > 0) {
+                if (vec4) {
+                    const int c4 = cols >> 2, P4 = rows * c4;
+                    const int csub = ptid & 3;
+                    for (int pos4 = ptid >> 2; pos4 < P4; pos4 += kPipeProducers / 4) {
+                        const int rr = pos4 / c4, x4 = pos4 - rr * c4;
+                        const float4* src = reinterpret_cast<const float4*>(
+                            base + (size_t)csub * plane + (size_t)(gy0 + rr) * g.W + x0 + 4 * x4);
+                        float* dp = pbuf + csub * pitch + 4 * pos4;
+                        float4 v[8];
+#pragma unroll
+                        for (int cg = 0; cg < 8; ++cg)
+                            if (cg * 4 + csub < nch) v[cg] = __ldg(src + (size_t)cg * plane);
+#pragma unroll
+                        for (int cg = 0; cg < 8; ++cg)
+                            if (cg * 4 + csub < nch) {
+                                float* d = dp + cg * 4 * pitch;
+                                d[0] = v[cg].x; d[1] = v[cg].y; d[2] = v[cg].z; d[3] = v[cg].w;
+                            }
+                    }
+                } else {
+                    for (int pos = ptid; pos < P; pos += kPipeProducers) {
+                        const int rr = pos / cols, x = pos - rr * cols;
+                        const float* src = base + (size_t)(gy0 + rr) * g.W + x0 + x;
+                        float* dp = pbuf + pos;
+                        int cc = 0;
+                        for (; cc + 8 <= nch; cc += 8) {
+                            float v[8];
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (size_t)q * plane);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) dp[q * pitch] = v[q];
+                            src += 8 * plane; dp += 8 * pitch;
+                        }
+                        for (; cc < nch; ++cc) { *dp = __ldg(src); src += plane; dp += pitch; }
+                    }
+                }
+            }
+            mbar_arrive(&bar_full[st]);                              // release: the staged data is visible to waiters
+        }
+    } else {
+        // =============================== CONSUMERS ===============================
+        for (int u = 0; u < nunits; ++u) {
+            const int chunk = u / ngroups, gi = u - chunk * ngroups;
+            const int st = u & 1;
+            const int rows = grp_rows[gi];
+            const int P = rows * cols;
+            const int pitch = P + ((33 - (P & 31)) & 31);
+            const int c0 = chunk * kChunk;
+            const int nch = min(kChunk, p.channels - c0);
+            float* ob = out_s + (chunk & 1) * obuf;
+            const int b0 = grp_ph0[gi] * PW, b1 = grp_ph0[gi + 1] * PW;
+            mbar_wait(&bar_full[st], (u >> 1) & 1);
+            if (grp_direct[gi]) {
+                const float* gp = feat + (size_t)(c0 + lane) * plane;
+                if (lane < nch)
+                    for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32) {
+                        int4 o4[4];
+                        for (int q = 0; q < 4; ++q) { o4[q] = tab_off[b * 4 + q]; o4[q].x >>= 2; o4[q].y >>= 2; o4[q].z >>= 2; o4[q].w >>= 2; }
+                        ob[lane * opitch + b] = bin_value<EXACT>(gp, o4, tab_w + b * 4);
+                    }
+            } else if (P == 0) {
+                for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32) ob[lane * opitch + b] = 0.0f;
+            } else if (lane < nch) {
+                const unsigned sbase = smem_u32(patch + st * patch_floats + lane * pitch);
+                for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32)
+                    ob[lane * opitch + b] = bin_value_smem<EXACT>(sbase, tab_off + b * 4, tab_w + b * 4);
+            }
+            mbar_arrive(&bar_empty[st]);                             // this thread is done reading the slot
+            if (gi == ngroups - 1) {
+                // all bins of the chunk are in ob: consumer-only barrier, then the coalesced write-out.
+                // The other output buffer is in use by the next chunk meanwhile; this one is rewritten
+                // only by chunk+2, whose bins start after the next consumer barrier.
+                asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory");
+                float* dst = dst_roi + (size_t)c0 * nbins;
+                const int total = nch * nbins;
+                if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+                    const float4* s4 = reinterpret_cast<const float4*>(ob);
+                    float4* d4 = reinterpret_cast<float4*>(dst);
+                    for (int i = tid; i < total / 4; i += kPipeConsumers) d4[i] = s4[i];
+                } else {
+                    for (int ch = warp; ch < nch; ch += kPipeConsumers / 32)
+                        for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
+                }
+            }
+        }
+    }
+}
+
 // Direct kernel: any sampling_ratio (incl. adaptive), any pooled size. One thread per output.
 __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_params p, const float* __restrict__ rois,
                                                          long long total, float* __restrict__ out,
@@ -610,6 +872,27 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
                         num_rois * chunks < (1ll << 31);
     if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
+        const char* sel = getenv("MB_ROI_KERNEL");
+        const bool legacy = sel != nullptr && strcmp(sel, "legacy") == 0;
+        if (!legacy) {
+            // 2 CTAs/SM: 2 output buffers + 2 footprint slots + bin tables within ~113 KB
+            const int obuf = (kChunk * opitch + 3) & ~3;
+            int pitch_cap = 353;
+            const char* pc = getenv("MB_ROI_PITCH");
+            if (pc != nullptr) pitch_cap = atoi(pc);
+            int smem = (2 * obuf + 2 * kChunk * pitch_cap) * (int)sizeof(float) + nbins * 4 * 32;
+            while (smem > 110 * 1024 && pitch_cap > 65) { pitch_cap -= 32; smem -= 2 * kChunk * 32 * (int)sizeof(float); }
+            const int patch_floats = kChunk * pitch_cap;
+            if (p.exact) {
+                MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                k_roi_align_sr2_pipe<true><<<(int)num_rois, kPipeThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+            } else {
+                MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                k_roi_align_sr2_pipe<false><<<(int)num_rois, kPipeThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+            }
+            MB_LAUNCH_CHECK();
+            return MB_OK;
+        }
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;

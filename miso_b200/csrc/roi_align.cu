@@ -356,11 +356,25 @@ __device__ __forceinline__ float bin_value(const float* sp, const int4* __restri
     return __fmul_rn(acc, 0.25f);   // acc / 4: exact scaling
 }
 
+// scalar staging: thread = footprint pixel, channels walked with U loads in flight
+template <int U>
+__device__ __forceinline__ void stage_scalar(const float* src, float* dp, size_t sstep, int dstep, int cc, int nch, int NG) {
+    for (; cc + (U - 1) * NG < nch; cc += U * NG) {
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(src + u * sstep);
+#pragma unroll
+        for (int u = 0; u < U; ++u) dp[u * dstep] = v[u];
+        src += U * sstep; dp += U * dstep;
+    }
+    for (; cc < nch; cc += NG) { *dp = __ldg(src); src += sstep; dp += dstep; }
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_align_params p,
                                                                 const float* __restrict__ rois,
                                                                 float* __restrict__ out, int* __restrict__ levels_out,
-                                                                int patch_floats) {
+                                                                int patch_floats, int variant) {
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[32], xtab[32];
     __shared__ int grp_ph0[kMaxGroups + 1], grp_y0[kMaxGroups], grp_rows[kMaxGroups], grp_direct[kMaxGroups];
@@ -389,7 +403,7 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
     const size_t plane = (size_t)g.H * g.W;
     const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
     // 16-byte vector staging needs every footprint row to start on a float4 boundary
-    const bool vec4 = ((g.W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
+    const bool vec4 = !(variant & 1) && ((g.W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
     int x0 = 0, x1 = -1;
     {
         int i = 0;
@@ -504,16 +518,8 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
                             float* dp = patch + grp * pitch + pos;
                             const size_t sstep = (size_t)NG * plane;
                             const int dstep = NG * pitch;
-                            int cc = grp;
-                            for (; cc + 7 * NG < nch; cc += 8 * NG) {
-                                float v[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + u * sstep);
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) dp[u * dstep] = v[u];
-                                src += 8 * sstep; dp += 8 * dstep;
-                            }
-                            for (; cc < nch; cc += NG) { *dp = __ldg(src); src += sstep; dp += dstep; }
+                            if (variant & 2) stage_scalar<16>(src, dp, sstep, dstep, grp, nch, NG);
+                            else stage_scalar<8>(src, dp, sstep, dstep, grp, nch, NG);
                         }
                     }
                 }
@@ -893,15 +899,17 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             MB_LAUNCH_CHECK();
             return MB_OK;
         }
+        const char* vs = getenv("MB_ROI_VARIANT");
+        const int variant = vs != nullptr ? atoi(vs) : 0;
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
         if (p.exact) {
             MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k_roi_align_sr2<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+            k_roi_align_sr2<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats, variant);
         } else {
             MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            k_roi_align_sr2<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
+            k_roi_align_sr2<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats, variant);
         }
         MB_LAUNCH_CHECK();
         return MB_OK;

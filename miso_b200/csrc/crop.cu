@@ -185,7 +185,7 @@ extern "C" int mb_crop_gather(const mb_crop_params* p, const int32_t* rects, con
     CropDev d;
     int rc = make_crop(*p, d, true);
     if (rc != MB_OK) return rc;
-    dim3 grid(kNumSMs, 8);
+    dim3 grid(kNumSMs * 2, 16);   // crop slots over x, row blocks over y: many short rows in flight
     k_crop_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(d, (const int4*)rects, src, (const long long*)offsets,
                                                          (long long*)totals, crops_out, crops_capacity_bytes);
     MB_LAUNCH_CHECK();

@@ -469,6 +469,80 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_small(SegArr
     if (tid == 0) s.seg_kept[g] = kept;
 }
 
+// Same sweep with the segment's whole mask preloaded into shared memory by all threads at once
+// (one latency hit with maximal memory-level parallelism) — used when n * ceil(n/64) words fit.
+static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                                          unsigned long long* __restrict__ keepbits, int max_keep) {
+    extern __shared__ unsigned long long rowsm[];   // [n][T]
+    __shared__ unsigned long long removed[kSweepSmallMaxWords];
+    __shared__ unsigned long long s_keepw;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = s.seg_count[g];
+    const int T = s.seg_words[g];
+    if (n == 0 || s.totals[2] != 0) { if (tid == 0) s.seg_kept[g] = 0; return; }
+    const unsigned long long* m = mask + s.mask_off[g];
+    unsigned long long* kb = keepbits + s.keep_off[g];
+    if (tid < T) removed[tid] = 0;
+    {   // rows are T words; only words >= the row's own block were written by the mask kernel
+        const int total = n * T;
+        int row = tid / T, col = tid - row * T;
+        const int drow = kSweepThreads / T, dcol = kSweepThreads - drow * T;
+        for (int idx = tid; idx < total; idx += kSweepThreads) {
+            if (col >= (row >> 6)) rowsm[idx] = __ldg(m + idx);
+            row += drow; col += dcol;
+            if (col >= T) { col -= T; ++row; }
+        }
+    }
+    __syncthreads();
+    int kept = 0;
+    for (int b = 0; b < T; ++b) {
+        const int nb = min(64, n - b * 64);
+        const unsigned long long* tile = rowsm + (size_t)(b * 64) * T + b;   // word(t, col) = tile[t*T + col]
+        if (warp == 0) {
+            const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
+            unsigned long long R = removed[b] | invalid, C = 0;
+            const int t0 = lane, t1 = lane + 32;
+            const unsigned long long s0 = (t0 < nb) ? (tile[t0 * T] & ((1ull << t0) - 1ull)) : 0ull;
+            const unsigned long long s1 = (t1 < nb) ? (tile[t1 * T] & ((1ull << t1) - 1ull)) : 0ull;
+            while ((C | R) != ~0ull) {
+                const unsigned long long D = C | R;
+                bool c0 = false, r0 = false, c1 = false, r1 = false;
+                if (!((D >> t0) & 1ull)) { if (s0 & C) r0 = true; else if ((s0 & ~R) == 0ull) c0 = true; }
+                if (!((D >> t1) & 1ull)) { if (s1 & C) r1 = true; else if ((s1 & ~R) == 0ull) c1 = true; }
+                C |= (unsigned long long)__ballot_sync(0xffffffffu, c0) | ((unsigned long long)__ballot_sync(0xffffffffu, c1) << 32);
+                R |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+            }
+            unsigned long long keepw = C;
+            if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
+                int extra = kept + __popcll(keepw) - max_keep;
+                while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+            }
+            if (lane == 0) { s_keepw = keepw; kb[b] = keepw; }
+        }
+        __syncthreads();
+        const unsigned long long keepw = s_keepw;
+        kept += __popcll(keepw);
+        if (max_keep > 0 && kept >= max_keep) {
+            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
+            break;
+        }
+        {
+            const int Wn = T - b;
+            const int col = 1 + (tid >> 2), q = tid & 3;
+            if (col < Wn) {
+                unsigned long long acc = 0, bits = (keepw >> (16 * q)) & 0xffffull;
+                while (bits) {
+                    const int t = __ffsll((long long)bits) - 1 + 16 * q; bits &= bits - 1;
+                    acc |= tile[t * T + col];
+                }
+                if (acc) atomicOr(&removed[b + col], acc);
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s.seg_kept[g] = kept;
+}
+
 inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsigned long long); }
 
 // Host helper: launch meta + mask + sweep on prepared sorted boxes.
@@ -478,6 +552,13 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     const float thr_up = strict_gt_threshold(iou_threshold);
     k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
+    const long long pre_bytes = (long long)max_seg_elems * ceil_div(max_seg_elems, 64) * 8;
+    if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords && pre_bytes <= 160 * 1024) {
+        MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_preload, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_bytes));
+        k_nms_sweep_preload<<<G, kSweepThreads, (int)pre_bytes, stream>>>(s, mask, keepbits, max_keep);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {
         k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);
         MB_LAUNCH_CHECK();

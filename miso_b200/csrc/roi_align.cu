@@ -356,6 +356,33 @@ __device__ __forceinline__ float bin_value(const float* sp, const int4* __restri
     return __fmul_rn(acc, 0.25f);   // acc / 4: exact scaling
 }
 
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <bool EXACT>
+__device__ __forceinline__ float bin_value_smem(unsigned sbase, const int4* __restrict__ toff, const float4* __restrict__ tw) {
+    // toff holds BYTE offsets; sbase is the lane's 32-bit shared address: one add per tap
+    float acc = 0.0f;
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int4 o = toff[smp];
+        const float4 wv = tw[smp];
+        float v1, v2, v3, v4;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(sbase + o.x));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(sbase + o.y));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(sbase + o.z));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4) : "r"(sbase + o.w));
+        if (EXACT) {
+            float t = __fmul_rn(wv.x, v1);
+            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
+            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
+            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
+            acc = __fadd_rn(acc, t);
+        } else {
+            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
+        }
+    }
+    return __fmul_rn(acc, 0.25f);
+}
+
 // scalar staging: thread = footprint pixel, channels walked with U loads in flight
 template <int U>
 __device__ __forceinline__ void stage_scalar(const float* src, float* dp, size_t sstep, int dstep, int cc, int nch, int NG) {
@@ -458,7 +485,7 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
         const int oy = direct ? 0 : grp_y0[gi], ox = direct ? 0 : x0;
         const int ylo = ok ? (Y.lo - oy) * rs : 0, yhi = ok ? (Y.hi - oy) * rs : 0;
         const int xlo = ok ? X.lo - ox : 0, xhi = ok ? X.hi - ox : 0;
-        tab_off[e] = make_int4(ylo + xlo, ylo + xhi, yhi + xlo, yhi + xhi);
+        tab_off[e] = make_int4(4 * (ylo + xlo), 4 * (ylo + xhi), 4 * (yhi + xlo), 4 * (yhi + xhi));   // byte offsets
         tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
                       : make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -530,14 +557,17 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
             if (direct) {
                 const float* gp = base + (size_t)lane * plane;            // global gathers (rare)
                 if (lane < nch)
-                    for (int b = b0 + warp; b < b1; b += kRoiWarps)
-                        out_s[lane * opitch + b] = bin_value<EXACT>(gp, tab_off + b * 4, tab_w + b * 4);
+                    for (int b = b0 + warp; b < b1; b += kRoiWarps) {
+                        int4 o4[4];
+                        for (int q = 0; q < 4; ++q) { o4[q] = tab_off[b * 4 + q]; o4[q].x >>= 2; o4[q].y >>= 2; o4[q].z >>= 2; o4[q].w >>= 2; }
+                        out_s[lane * opitch + b] = bin_value<EXACT>(gp, o4, tab_w + b * 4);
+                    }
             } else if (P == 0) {              // no valid sample row in this group: zeros (nothing was staged)
                 for (int b = b0 + warp; b < b1; b += kRoiWarps) out_s[lane * opitch + b] = 0.0f;
             } else if (lane < nch) {
-                const float* sp = patch + lane * pitch;                   // shared memory: LDS, 32-bit addresses
+                const unsigned sbase = smem_u32(patch + lane * pitch);    // 32-bit shared address: one add per tap
                 for (int b = b0 + warp; b < b1; b += kRoiWarps)
-                    out_s[lane * opitch + b] = bin_value<EXACT>(sp, tab_off + b * 4, tab_w + b * 4);
+                    out_s[lane * opitch + b] = bin_value_smem<EXACT>(sbase, tab_off + b * 4, tab_w + b * 4);
             }
             __syncthreads();
         }
@@ -566,7 +596,6 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
 // ------------------------------------------------------------------------------------------
 constexpr int kPipeConsumers = 256, kPipeProducers = 128, kPipeThreads = kPipeConsumers + kPipeProducers;
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -583,32 +612,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
         if (done) break;
         if (++spins > (1 << 26)) __trap();   // a protocol bug must fault, never hang the GPU
     }
-}
-
-template <bool EXACT>
-__device__ __forceinline__ float bin_value_smem(unsigned sbase, const int4* __restrict__ toff, const float4* __restrict__ tw) {
-    // toff holds BYTE offsets; sbase is the lane's 32-bit shared address: one add per tap
-    float acc = 0.0f;
-#pragma unroll
-    for (int smp = 0; smp < 4; ++smp) {
-        const int4 o = toff[smp];
-        const float4 wv = tw[smp];
-        float v1, v2, v3, v4;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(sbase + o.x));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(sbase + o.y));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(sbase + o.z));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4) : "r"(sbase + o.w));
-        if (EXACT) {
-            float t = __fmul_rn(wv.x, v1);
-            t = __fadd_rn(t, __fmul_rn(wv.y, v2));
-            t = __fadd_rn(t, __fmul_rn(wv.z, v3));
-            t = __fadd_rn(t, __fmul_rn(wv.w, v4));
-            acc = __fadd_rn(acc, t);
-        } else {
-            acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
-        }
-    }
-    return __fmul_rn(acc, 0.25f);
 }
 
 template <bool EXACT>
@@ -879,7 +882,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
         const char* sel = getenv("MB_ROI_KERNEL");
-        const bool legacy = sel != nullptr && strcmp(sel, "legacy") == 0;
+        const bool legacy = sel == nullptr || strcmp(sel, "pipe") != 0;   // the single-role kernel measured faster (profiles/)
         if (!legacy) {
             // 2 CTAs/SM: 2 output buffers + 2 footprint slots + bin tables within ~113 KB
             const int obuf = (kChunk * opitch + 3) & ~3;
@@ -900,7 +903,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             return MB_OK;
         }
         const char* vs = getenv("MB_ROI_VARIANT");
-        const int variant = vs != nullptr ? atoi(vs) : 0;
+        const int variant = vs != nullptr ? atoi(vs) : 2;   // bit0: no float4 staging, bit1: 16 scalar loads in flight
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;

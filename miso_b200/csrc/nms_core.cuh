@@ -483,14 +483,25 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegA
     const unsigned long long* m = mask + s.mask_off[g];
     unsigned long long* kb = keepbits + s.keep_off[g];
     if (tid < T) removed[tid] = 0;
-    {   // rows are T words; only words >= the row's own block were written by the mask kernel
+    {   // rows are T words; only words >= the row's own block were written by the mask kernel.
+        // 8 independent loads are issued before the first store (memory-level parallelism).
         const int total = n * T;
-        int row = tid / T, col = tid - row * T;
-        const int drow = kSweepThreads / T, dcol = kSweepThreads - drow * T;
-        for (int idx = tid; idx < total; idx += kSweepThreads) {
-            if (col >= (row >> 6)) rowsm[idx] = __ldg(m + idx);
-            row += drow; col += dcol;
-            if (col >= T) { col -= T; ++row; }
+        for (int base = 0; base < total; base += 8 * kSweepThreads) {
+            unsigned long long v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kSweepThreads + tid;
+                v[u] = 0;
+                if (idx < total) {
+                    const int row = idx / T, col = idx - row * T;
+                    if (col >= (row >> 6)) v[u] = __ldg(m + idx);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kSweepThreads + tid;
+                if (idx < total) rowsm[idx] = v[u];
+            }
         }
     }
     __syncthreads();

@@ -250,14 +250,17 @@ def run_ours(args):
     n, dpi = args.batch, hp.dpi
     # mosaic framing for N > 1: this rank's images are tiles at (row=rank, col=i) of a tile grid with 128 px overlap
     origins = torch.tensor([[rank * 896.0, i * 896.0] for i in range(n)], dtype=torch.float32, device=dev)
-    seam_launches = 0
+    seam = mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev) if world > 1 else None
+
+    def exchange_and_seam():
+        # fixed-size blocks -> one all_gather_into_tensor -> seam NMS on the same stream, no host sync
+        block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
+        seam.launch(mosaic.exchange(block, world), w.det.nms_thresh)
 
     def step():
         hp.step()
         if world > 1:
-            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
-            gathered = mosaic.exchange(block, world)
-            return mosaic.seam_nms(gathered, w.det.nms_thresh)
+            exchange_and_seam()
         return None
 
     for _ in range(max(args.warmup, 3)):
@@ -286,8 +289,7 @@ def run_ours(args):
         hp.detections(st)
         hp.crops(st)
         if world > 1:
-            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
-            mosaic.seam_nms(mosaic.exchange(block, world), w.det.nms_thresh)
+            exchange_and_seam()
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -322,8 +324,8 @@ def run_ours(args):
         nb = int(host_out["crop_totals"][1])
         host_pix[:nb].copy_(hp.crop_pixels[:nb], non_blocking=True)
         if world > 1:
-            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
-            b, s, l = mosaic.seam_nms(mosaic.exchange(block, world), w.det.nms_thresh)
+            exchange_and_seam()
+            b, s, l = seam.finish()
             b.cpu()
         torch.cuda.synchronize()
         return nb

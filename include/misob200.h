@@ -49,7 +49,8 @@ const char* mb_build_info(void);
  * semantics of the CPU kernel tv-csrc:ops/cpu/nms_kernel.cpp:116) and both batched_nms
  * strategies (tv:ops/boxes.py:86-120).
  *   mode 0  plain nms (groups ignored)
- *   mode 1  per-group NMS on raw coordinates ("vanilla"); groups[i] in [0, num_groups)
+ *   mode 1  per-group NMS on raw coordinates ("vanilla"); groups[i] in [0, num_groups);
+ *           rows with a negative group are ignored (padding of fixed-capacity inputs)
  *   mode 2  coordinate trick: boxes + fl(fl(group) * fl(max(boxes) + 1)), then plain nms
  * keep_out [num_boxes] receives original indices in descending-score order (ties: lower
  * index first). status_out[0] = number kept, or -1 if the mask workspace was too small, in

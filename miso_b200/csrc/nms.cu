@@ -63,7 +63,8 @@ __global__ void k_group_hist(const long long* __restrict__ groups, long long K, 
                              unsigned int* bad_flag) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < K; i += (long long)gridDim.x * blockDim.x) {
         const long long g = groups[i];
-        if (g < 0 || g >= G) { *bad_flag = 1u; continue; }
+        if (g < 0) continue;                       // negative group: row is not a box (padding), ignored
+        if (g >= G) { *bad_flag = 1u; continue; }
         atomicAdd(&seg_count[(int)g], 1);
     }
 }

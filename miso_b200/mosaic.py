@@ -75,6 +75,30 @@ def exchange(block: Tensor, world: int, group=None) -> Tensor:
     return out
 
 
+class SeamNms:
+    """Sync-free seam NMS for CUDA tensors: one prepared mb_nms launch sequence over ALL gathered
+    rows (padding rows carry label -1 and are ignored on the device), enqueued on the same stream
+    right behind the all-gather. `finish()` reads the count (the step's only host sync)."""
+
+    def __init__(self, rows: int, num_classes: int, device):
+        from .ops import PreparedBatchedNms
+        self.nms = PreparedBatchedNms(rows, num_classes, device)
+        self.gathered = None
+
+    def launch(self, gathered: Tensor, iou_threshold: float):
+        self.gathered = gathered
+        self.boxes = gathered[:, :4].contiguous()
+        self.scores = gathered[:, 4].contiguous()
+        self.labels = gathered[:, 5].to(torch.int64)
+        return self.nms(self.boxes, self.scores, self.labels, iou_threshold)
+
+    def finish(self):
+        keep, status = self.nms.keep, self.nms.status
+        n = int(status[0])
+        keep = keep[:n]
+        return self.boxes[keep], self.scores[keep], self.labels[keep]
+
+
 def seam_nms(gathered: Tensor, iou_threshold: float, nms_fn: Optional[Callable] = None):
     """Cross-tile NMS over every live row, always the per-class ("vanilla") strategy on raw
     mosaic coordinates. Returns (boxes, scores, labels) in (score desc, gathered order asc) order."""

@@ -94,6 +94,29 @@ def _nms_impl(boxes: Tensor, scores: Tensor, groups: Optional[Tensor], num_group
     raise MisoB200Error("mb_nms: mask workspace negotiation failed")
 
 
+class PreparedBatchedNms:
+    """Fixed-capacity, sync-free per-category NMS: workspaces and outputs are allocated once, rows
+    whose category is negative are ignored (padding), the kept indices and their count stay on
+    the device. Used for the cross-tile seam NMS right behind the NCCL all-gather."""
+
+    def __init__(self, capacity: int, num_groups: int, device):
+        self.lib = _lib.load()
+        self.k, self.g = int(capacity), int(num_groups)
+        self.keep = torch.empty((self.k,), dtype=torch.int64, device=device)
+        self.status = torch.zeros((4,), dtype=torch.int64, device=device)
+        self.ws = _workspace(self.lib.mb_nms_workspace_bytes(self.k, self.g), device)
+        self.mask = _workspace(self.k * ((self.k + 63) // 64) * 8, device)     # exact single-segment bound
+
+    def __call__(self, boxes: Tensor, scores: Tensor, groups: Tensor, iou_threshold: float):
+        """boxes [K,4] fp32, scores [K] fp32, groups [K] int64 (negative = ignore), all contiguous.
+        Returns (keep, status) device tensors: status[0] = number kept (no host sync here)."""
+        rc = self.lib.mb_nms(_ptr(boxes), _ptr(scores), _ptr(groups), self.k, self.g, 1, float(iou_threshold),
+                             _ptr(self.keep), _ptr(self.status), _ptr(self.ws), self.ws.numel(), _ptr(self.mask),
+                             self.mask.numel(), _stream(boxes))
+        _lib.check(rc, "mb_nms")
+        return self.keep, self.status
+
+
 def nms(boxes: Tensor, scores: Tensor, iou_threshold: float) -> Tensor:
     """Greedy NMS; int64 indices of kept boxes in descending score order (ties: lower index
     first). Semantics of the torchvision CPU kernel: fp32 IoU, `(double)iou > iou_threshold`."""

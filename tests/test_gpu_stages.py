@@ -198,3 +198,25 @@ def test_crop_full_size_roundtrip(det):
     assert len(crops) == len(ref)
     for (n, i, xywh, arr), r in zip(crops, ref):
         assert arr.shape == r.shape and np.array_equal(arr, r)
+
+
+def test_seam_nms_sync_free_equals_compacting_version(det):
+    """mosaic.SeamNms (padding rows ignored on the device, no host sync before finish) must give
+    exactly the result of the compacting seam_nms and of the oracle's per-class NMS."""
+    from miso_b200 import mosaic
+    from tests.test_mosaic_cpu import synth_tiles
+    b, s, l, c, o = synth_tiles(num_tiles=6, dpi=60, seed=3)
+    block = mosaic.pack_block(cu(b), cu(s), cu(l), cu(c).to(torch.int32), cu(o), 0.5, 6 * 60 + 17)
+    ref_b, ref_s, ref_l = mosaic.seam_nms(block, 0.5)
+    seam = mosaic.SeamNms(block.shape[0], 3, DEV)
+    seam.launch(block, 0.5)
+    gb, gs, gl = seam.finish()
+    assert torch.equal(gb, ref_b) and torch.equal(gs, ref_s) and torch.equal(gl, ref_l)
+    live = block[:, 5] >= 0
+    rows = block[live].cpu().numpy()
+    keep = D.batched_nms_vanilla(rows[:, :4], rows[:, 4], rows[:, 5].astype(np.int64), 0.5)
+    assert np.array_equal(gb.cpu().numpy(), rows[keep, :4])
+    # idempotent and reusable
+    seam.launch(block, 0.5)
+    gb2, _, _ = seam.finish()
+    assert torch.equal(gb2, gb)

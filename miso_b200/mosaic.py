@@ -109,3 +109,52 @@ def seam_nms(gathered: Tensor, iou_threshold: float, nms_fn: Optional[Callable] 
     boxes, scores, labels = rows[:, :4].contiguous(), rows[:, 4].contiguous(), rows[:, 5].to(torch.int64)
     keep = nms_fn(boxes, scores, labels, iou_threshold)
     return boxes[keep], scores[keep], labels[keep]
+
+
+def infer_mosaic(model, mosaic_u8: Tensor, tile: int = 1024, overlap: int = 128, threshold: float = 0.5,
+                 batch_size: int = 4, rank: int = 0, world: int = 1, crops: bool = True):
+    """Detect on a large slide/mosaic image (config 5): cut it into overlapping tiles, run this
+    rank's contiguous share of tiles through the (patched) model, exchange the per-rank detection
+    blocks with one all-gather, run the seam NMS and cut the crops of the surviving detections.
+
+    mosaic_u8: uint8 [H, W, C] on the device (every rank holds the pixels it needs; here the whole
+    mosaic). Returns (boxes [M,4] in mosaic coordinates, scores [M], labels [M], crops) where crops
+    is the CropOutput of this rank's share (detections rank::world) or None."""
+    from . import detection
+    dev = mosaic_u8.device
+    h, w = int(mosaic_u8.shape[0]), int(mosaic_u8.shape[1])
+    grid = tile_grid(h, w, tile, overlap)
+    mine = list(rank_tiles(len(grid), world, rank))
+    dpi = int(model.roi_heads.detections_per_img)
+    tmax = tiles_per_rank_max(len(grid), world)
+    boxes = torch.zeros((len(mine), dpi, 4), dtype=torch.float32, device=dev)
+    scores = torch.zeros((len(mine), dpi), dtype=torch.float32, device=dev)
+    labels = torch.zeros((len(mine), dpi), dtype=torch.int64, device=dev)
+    counts = torch.zeros((len(mine),), dtype=torch.int32, device=dev)
+    with torch.inference_mode():
+        for i0 in range(0, len(mine), batch_size):
+            idx = mine[i0:i0 + batch_size]
+            imgs = []
+            for t in idx:
+                y, x = grid[t]
+                imgs.append(mosaic_u8[y:y + tile, x:x + tile].permute(2, 0, 1).to(torch.float32) / 255)
+            res = model(imgs)
+            for j, r in enumerate(res):
+                k = int(r["boxes"].shape[0])
+                boxes[i0 + j, :k], scores[i0 + j, :k], labels[i0 + j, :k] = r["boxes"], r["scores"], r["labels"]
+                counts[i0 + j] = k
+    origins = torch.tensor([[float(grid[t][0]), float(grid[t][1])] for t in mine], dtype=torch.float32, device=dev).reshape(-1, 2)
+    block = pack_block(boxes, scores, labels, counts, origins, threshold, tmax * dpi)
+    gathered = exchange(block, world)
+    num_classes = int(model.roi_heads.box_predictor.cls_score.out_features)
+    seam = SeamNms(gathered.shape[0], num_classes, dev)
+    seam.launch(gathered, float(model.roi_heads.nms_thresh))
+    fb, fs, fl = seam.finish()
+    out_crops = None
+    if crops:
+        share = torch.arange(rank, fb.shape[0], world, device=dev)
+        sb = fb[share]
+        if sb.shape[0] > 0:
+            out_crops = detection.filter_and_crop([mosaic_u8], sb[None].contiguous(), torch.ones((1, sb.shape[0]), device=dev),
+                                                  torch.tensor([sb.shape[0]], dtype=torch.int32, device=dev), 0.5)
+    return fb, fs, fl, out_crops

@@ -204,3 +204,37 @@ def test_cli_infer_directory_writes_reference_crops(tmp_path):
         found = any(np.array_equal(crop, src[yy:yy + crop.shape[0], xx:xx + crop.shape[1]])
                     for yy in range(max(ys - 1, 0), ys + 2) for xx in range(max(xs - 1, 0), xs + 2))
         assert found
+
+
+def test_infer_mosaic_equals_per_tile_composition():
+    """Config 5 driver on a small mosaic (4 overlapping tiles): its result must equal the explicit
+    composition: per-tile detections of the same model -> + tile origin -> score filter -> the
+    oracle's per-class NMS -> the oracle's crops."""
+    from miso_b200 import mosaic
+    from miso_b200.patch import patch_model
+    model = patch_model(make_model("faster").to(DEV))
+    g = torch.Generator().manual_seed(5)
+    mos = torch.randint(0, 256, (1536, 1536, 3), dtype=torch.uint8, generator=g)
+    mos_dev = mos.to(DEV)
+    thr = 0.3
+    fb, fs, fl, crops = mosaic.infer_mosaic(model, mos_dev, tile=1024, overlap=128, threshold=thr, batch_size=2)
+    grid = mosaic.tile_grid(1536, 1536, 1024, 128)
+    assert grid == [(0, 0), (0, 512), (512, 0), (512, 512)]
+    allb, alls, alll = [], [], []
+    with torch.inference_mode():
+        for i0 in range(0, 4, 2):
+            imgs = [mos_dev[y:y + 1024, x:x + 1024].permute(2, 0, 1).to(torch.float32) / 255 for y, x in grid[i0:i0 + 2]]
+            for (y, x), r in zip(grid[i0:i0 + 2], model(imgs)):
+                off = torch.tensor([x, y, x, y], dtype=torch.float32, device=DEV)
+                m = r["scores"] > thr
+                allb.append((r["boxes"] + off)[m]); alls.append(r["scores"][m]); alll.append(r["labels"][m])
+    B, S, L = torch.cat(allb).cpu().numpy(), torch.cat(alls).cpu().numpy(), torch.cat(alll).cpu().numpy()
+    from oracle import detection as D
+    keep = D.batched_nms_vanilla(B, S, L, float(model.roi_heads.nms_thresh))
+    assert np.array_equal(fb.cpu().numpy(), B[keep]) and np.array_equal(fl.cpu().numpy(), L[keep])
+    assert len(keep) > 0
+    got = crops.to_host(3)
+    _, _, _, _, _, ref = M.filter_and_crop(mos.numpy(), B[keep], np.ones(len(keep), np.float32), L[keep], 0.5)
+    assert len(got) == len(ref)
+    for (_, _, _, a), r in zip(got, ref):
+        assert np.array_equal(a, r)

@@ -95,6 +95,10 @@ typedef struct {
      * box_counts (device, nullable) gives the live rows per image, rows beyond it produce zeros. */
     int32_t boxes_per_image;
     const int32_t* box_counts;
+    /* != 0: every feature map is stored channels-last ([N, H, W, C] in memory — what a
+     * torch.channels_last cuDNN backbone produces). The kernel then gathers 128-byte channel
+     * vectors straight from global memory / L1 and needs no shared-memory staging. */
+    int32_t channels_last;
 } mb_roi_align_params;
 size_t mb_roi_align_workspace_bytes(int64_t num_rois);
 int mb_multiscale_roi_align(const mb_roi_align_params* params_host, const float* rois, int64_t num_rois,

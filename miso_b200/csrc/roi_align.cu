@@ -820,6 +820,104 @@ __global__ void __launch_bounds__(kPipeThreads, 2) k_roi_align_sr2_pipe(const mb
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Channels-last features ([N, H, W, C] in memory): no staging at all. A tap of 32 consecutive
+// channels is one 128-byte line, so "lane = channel" gathers are perfectly coalesced straight from
+// global memory; the footprint of one 32-channel chunk (~330 pixels x 128 B) lives in L1 while the
+// CTA's 8 warps work through the chunk's 49 bins (each pixel is touched ~2.4 times). There are no
+// load/compute phases and only one barrier per chunk (output hand-over), so warps overlap their
+// own global-load latency with 16 independent loads per bin.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_nhwc(const mb_roi_align_params p,
+                                                                 const float* __restrict__ rois,
+                                                                 float* __restrict__ out, int* __restrict__ levels_out) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ Tap ytab[32], xtab[32];
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
+    const int opitch = (nbins & 1) ? nbins : nbins + 1;
+    const int obuf = (kChunk * opitch + 3) & ~3;
+    float* out_s = smem;                                               // [2][kChunk][opitch]
+    int4* tab_off = reinterpret_cast<int4*>(out_s + 2 * obuf);        // [nbins][4] byte offsets of the pixel's channel vector
+    float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);   // [nbins][4]
+
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);
+    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
+    const int ny = PH * 2, nx = PW * 2;
+    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
+    if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
+    __syncthreads();
+    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
+    const int C = p.channels;
+    float* dst_roi = out + (size_t)k * C * nbins;
+    if (bad_batch) {
+        for (long long i = tid; i < (long long)C * nbins; i += kRoiThreads) dst_roi[i] = 0.0f;
+        return;
+    }
+    for (int e = tid; e < nbins * 4; e += kRoiThreads) {
+        const int b = e >> 2, smp = e & 3;
+        const int ph = b / PW, pw = b - ph * PW;
+        const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
+        const bool ok = Y.valid && X.valid;
+        const int cb = C * 4;   // bytes per pixel
+        const int ylo = ok ? Y.lo * g.W : 0, yhi = ok ? Y.hi * g.W : 0;
+        const int xlo = ok ? X.lo : 0, xhi = ok ? X.hi : 0;
+        tab_off[e] = make_int4((ylo + xlo) * cb, (ylo + xhi) * cb, (yhi + xlo) * cb, (yhi + xhi) * cb);
+        tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const char* img = reinterpret_cast<const char*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C * 4;
+    const int nchunks = (C + kChunk - 1) / kChunk;
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int c0 = chunk * kChunk;
+        const int nch = min(kChunk, C - c0);
+        float* ob = out_s + (chunk & 1) * obuf;
+        if (lane < nch) {
+            const char* gp = img + (size_t)(c0 + lane) * 4;
+            for (int b = warp; b < nbins; b += kRoiWarps) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int smp = 0; smp < 4; ++smp) {
+                    const int4 o = tab_off[b * 4 + smp];
+                    const float4 wv = tab_w[b * 4 + smp];
+                    const float v1 = __ldg(reinterpret_cast<const float*>(gp + o.x));
+                    const float v2 = __ldg(reinterpret_cast<const float*>(gp + o.y));
+                    const float v3 = __ldg(reinterpret_cast<const float*>(gp + o.z));
+                    const float v4 = __ldg(reinterpret_cast<const float*>(gp + o.w));
+                    if (EXACT) {
+                        float t = __fmul_rn(wv.x, v1);
+                        t = __fadd_rn(t, __fmul_rn(wv.y, v2));
+                        t = __fadd_rn(t, __fmul_rn(wv.z, v3));
+                        t = __fadd_rn(t, __fmul_rn(wv.w, v4));
+                        acc = __fadd_rn(acc, t);
+                    } else {
+                        acc = fmaf(wv.x, v1, fmaf(wv.y, v2, fmaf(wv.z, v3, fmaf(wv.w, v4, acc))));
+                    }
+                }
+                ob[lane * opitch + b] = __fmul_rn(acc, 0.25f);
+            }
+        }
+        __syncthreads();   // the chunk's bins are complete; the other buffer is free for the next chunk
+        float* dst = dst_roi + (size_t)c0 * nbins;
+        const int total = nch * nbins;
+        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(ob);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = tid; i < total / 4; i += kRoiThreads) d4[i] = s4[i];
+        } else {
+            for (int ch = warp; ch < nch; ch += kRoiWarps)
+                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
+        }
+        // buffer (chunk & 1) is rewritten by chunk + 2, after the barrier of chunk + 1
+    }
+}
+
 // Direct kernel: any sampling_ratio (incl. adaptive), any pooled size. One thread per output.
 __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_params p, const float* __restrict__ rois,
                                                          long long total, float* __restrict__ out,
@@ -879,6 +977,22 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     const bool staged = p.sampling_ratio > 0 && p.sampling_ratio * p.pooled_h <= kMaxSamples &&
                         p.sampling_ratio * p.pooled_w <= kMaxSamples && nbins <= 512 &&
                         num_rois * chunks < (1ll << 31);
+    if (p.channels_last) {
+        if (!(p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)))
+            return MB_ERR_UNSUPPORTED;   // the host converts to NCHW for other configurations
+        const int opitch = (nbins & 1) ? nbins : nbins + 1;
+        const int obuf = (kChunk * opitch + 3) & ~3;
+        const int smem = 2 * obuf * (int)sizeof(float) + nbins * 4 * 32;
+        if (p.exact) {
+            MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_roi_align_nhwc<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out);
+        } else {
+            MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            k_roi_align_nhwc<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out);
+        }
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
         const char* sel = getenv("MB_ROI_KERNEL");

@@ -294,9 +294,14 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
         p.pooled_h, p.pooled_w, p.sampling_ratio = ph, pw, int(sampling_ratio)
         p.aligned, p.exact = int(bool(aligned)), int(bool(exact))
         keepalive = []
+        # channels-last maps (what a torch.channels_last backbone produces) are consumed in place
+        nhwc = (int(sampling_ratio) == 2 and ph <= 16 and pw <= 16 and c > 1 and
+                all(f.dtype == torch.float32 and not f.is_contiguous() and
+                    f.is_contiguous(memory_format=torch.channels_last) for f in features))
+        p.channels_last = int(nhwc)
         for i, f in enumerate(features):
             torch._assert(f.shape[0] == n and f.shape[1] == c, "all feature maps must share batch and channel sizes")
-            fc = _f32c(f)
+            fc = f.detach() if nhwc else _f32c(f)
             keepalive.append(fc)
             p.height[i], p.width[i] = fc.shape[2], fc.shape[3]
             p.spatial_scale[i] = float(scales[i])

@@ -185,3 +185,26 @@ def test_grid_anchors(ops, golden_dir):
         base = ops.base_anchors(cases.RPN_SIZES[lvl], cases.RPN_RATIOS[lvl])
         outs.append(ops.grid_anchors(base, (gh, gw), (224 // gh, 288 // gw), DEV).cpu().numpy())
     assert np.array_equal(np.concatenate(outs), g["anchors"])
+
+
+def test_roi_align_channels_last_features_bit_identical(ops, golden_dir):
+    """Feature maps in torch.channels_last memory format are consumed in place by the NHWC kernel;
+    the result must be bit-identical to the NCHW path (and hence to the CPU reference)."""
+    g = load(golden_dir, "multiscale_box7")
+    feats, boxes, shapes = cases.multiscale_case()
+    pool = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)
+    x_nchw = {str(i): cu(f) for i, f in enumerate(feats)}
+    x_nhwc = {k: v.contiguous(memory_format=torch.channels_last) for k, v in x_nchw.items()}
+    assert not x_nhwc["0"].is_contiguous()
+    b = [cu(bb) for bb in boxes]
+    a = pool(x_nchw, b, shapes)
+    c = pool(x_nhwc, b, shapes)
+    assert torch.equal(a, c)
+    assert np.array_equal(c.cpu().numpy()[:, ::4], g["out"])
+    assert c.is_contiguous()                               # output stays [K, C, P, P] contiguous for the box head
+    for name, x, rois, scale, P, sr, aligned in cases.roi_align_cases():
+        if sr != 2:
+            continue
+        xc = cu(x).contiguous(memory_format=torch.channels_last)
+        out = ops.roi_align(xc, cu(rois), P, scale, sr, aligned).cpu().numpy()
+        assert np.array_equal(out, native.roi_align(x, rois, scale, P, P, sr, aligned)), name

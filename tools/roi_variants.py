@@ -48,10 +48,12 @@ for P, per in ((7, 1000), (14, 100)):
             ref = out.clone()
         res[f"P{P}_{name}"] = {"ms": timeit(fn), "same": bool(torch.equal(out, ref))}
     feats_cl = [f.contiguous(memory_format=torch.channels_last) for f in feats]
-    for exact in (True, False):
+    for nv in ("scalar", "vec"):
+      os.environ["MB_ROI_NHWC"] = nv
+      for exact in (True, False):
         fn = lambda: ops._roi_align_launch(feats_cl, rois, pool.scales, pool.thresholds, pool.output_size, 2, False, exact)
         out = fn()
-        res[f"P{P}_nhwc_exact{int(exact)}"] = {"ms": timeit(fn), "same": bool(torch.equal(out, ref)) if exact else bool(torch.allclose(out, ref, rtol=1e-5, atol=5e-5))}
+        res[f"P{P}_nhwc_{nv}_exact{int(exact)}"] = {"ms": timeit(fn), "same": bool(torch.equal(out, ref)) if exact else bool(torch.allclose(out, ref, rtol=1e-5, atol=5e-5))}
 print(json.dumps(res, indent=1))
 with open(os.path.join(ROOT, "gpurun_out", "roi_variants.json"), "w") as fh:
     json.dump(res, fh, indent=1)

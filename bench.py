@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--fast-roi-align", action="store_true", help="FMA RoIAlign (<=1e-5) instead of the bit-exact order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--features-layout", default="channels_last", choices=["channels_last", "nchw"],
+                    help="memory format of the synthetic FPN maps: channels_last = what a torch.channels_last "
+                         "cuDNN backbone produces (gathered in place); nchw = the reference's default layout")
     return ap.parse_args()
 
 
@@ -242,7 +245,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = workload.faster_rcnn_batch(num_images=args.batch, seed=rank)
+    w = workload.faster_rcnn_batch(num_images=args.batch, seed=rank, features_layout=args.features_layout)
     hp = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=512 << 20,
                           exact_roi_align=not args.fast_roi_align, device=dev)
     d = workload.to_device(w, dev)
@@ -378,11 +381,13 @@ def run_ours(args):
     scl = [q.spatial_scale[i] for i in range(q.num_levels)]
     alg_bytes, k_live, touched = roi_align_algorithmic_bytes(props, cnts, w.shapes, thr, scl, w.shapes.channels, w.shapes.pooled)
     achieved = alg_bytes / (roi_mean_ms * 1e-3) / 1e9
+    nchw_route = "k_nchw_to_nhwc+k_roi_align_nhwc4" if hp.roi_ws is not None else "k_roi_align_sr2"
+    roi_kernel = "k_roi_align_nhwc4" if hp.features_layout == "channels_last" else nchw_route
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("dram_bytes_per_launch")
+            traffic = json.load(fh).get(roi_kernel, {}).get("dram_bytes_per_launch")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_port(w)
@@ -390,11 +395,11 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": w.name, "per_gpu_batch": args.batch, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
+        "config": {"workload": w.name, "per_gpu_batch": args.batch, "features_layout": hp.features_layout, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
                    "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step on a second stream (overlaps the next batch)" if world > 1 else "single GPU",
                    "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
-        "roofline": {"bound": "hbm", "kernel": "k_roi_align_staged", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
                      "kernel_share_of_step": roi_mean_ms / ms_per_step},

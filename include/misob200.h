@@ -100,7 +100,9 @@ typedef struct {
      * vectors straight from global memory / L1 and needs no shared-memory staging. */
     int32_t channels_last;
 } mb_roi_align_params;
-size_t mb_roi_align_workspace_bytes(int64_t num_rois);
+/* Optional workspace: when non-zero and provided, NCHW maps are transposed once to channels-last and
+ * gathered from there (faster when the RoIs' footprints cover the pyramid several times over). */
+size_t mb_roi_align_workspace_bytes(const mb_roi_align_params* params_host, int64_t num_rois);
 int mb_multiscale_roi_align(const mb_roi_align_params* params_host, const float* rois, int64_t num_rois,
                             float* out, int32_t* levels_out /* nullable, [K] */, void* workspace,
                             size_t workspace_bytes, mb_stream_t stream);

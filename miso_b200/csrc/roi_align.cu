@@ -1019,6 +1019,30 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
     }
 }
 
+// NCHW -> channels-last transpose of one feature map ([N][C][HW] -> [N][HW][C]), 32x32 tiles through
+// shared memory: reads coalesced along HW, writes coalesced along C. Used when the total footprint
+// volume of the RoIs is several times the size of the pyramid: one pass over the maps (read + write)
+// is then cheaper than staging every RoI's footprint from the NCHW planes.
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float* __restrict__ in, float* __restrict__ outp, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int hw0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 rows per pass
+    const float* src = in + (size_t)n * C * HW;
+    float* dst = outp + (size_t)n * C * HW;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, hw = hw0 + tx;
+        if (c < C && hw < HW) tile[r][tx] = __ldg(src + (size_t)c * HW + hw);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int hw = hw0 + r, c = c0 + tx;
+        if (c < C && hw < HW) dst[(size_t)hw * C + c] = tile[tx][r];
+    }
+}
+
 // Direct kernel: any sampling_ratio (incl. adaptive), any pooled size. One thread per output.
 __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_params p, const float* __restrict__ rois,
                                                          long long total, float* __restrict__ out,
@@ -1058,14 +1082,27 @@ __global__ void __launch_bounds__(256) k_roi_align_direct(const mb_roi_align_par
 
 using namespace mb;
 
-extern "C" size_t mb_roi_align_workspace_bytes(int64_t) { return 256; }
+static size_t nhwc_copy_bytes(const mb_roi_align_params& p) {
+    size_t b = 0;
+    for (int l = 0; l < p.num_levels; ++l)
+        b += align_up((size_t)p.num_images * p.channels * p.height[l] * p.width[l] * sizeof(float), 256);
+    return b;
+}
+
+// Workspace that lets NCHW inputs take the transpose + channels-last gather route (0 if not applicable).
+extern "C" size_t mb_roi_align_workspace_bytes(const mb_roi_align_params* pp, int64_t num_rois) {
+    if (!pp || pp->channels_last || pp->sampling_ratio != 2 || pp->pooled_h > 16 || pp->pooled_w > 16 || pp->channels % 4) return 0;
+    const double footprint = (double)num_rois * pp->channels * 320.0 * sizeof(float);   // ~320 pixels per RoI and channel
+    const size_t maps = nhwc_copy_bytes(*pp);
+    return footprint >= 1.5 * (double)maps ? maps + 256 : 0;
+}
 
 extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const float* rois, int64_t num_rois,
-                                       float* out, int32_t* levels_out, void* /*workspace*/,
-                                       size_t /*workspace_bytes*/, mb_stream_t stream_) {
+                                       float* out, int32_t* levels_out, void* workspace,
+                                       size_t workspace_bytes, mb_stream_t stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!pp) return MB_ERR_INVALID_ARG;
-    const mb_roi_align_params p = *pp;
+    mb_roi_align_params p = *pp;
     if (p.num_levels < 1 || p.num_levels > MB_MAX_LEVELS || p.channels < 1 || p.pooled_h < 1 || p.pooled_w < 1 ||
         p.num_images < 1 || num_rois < 0)
         return MB_ERR_INVALID_ARG;
@@ -1078,6 +1115,22 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     const bool staged = p.sampling_ratio > 0 && p.sampling_ratio * p.pooled_h <= kMaxSamples &&
                         p.sampling_ratio * p.pooled_w <= kMaxSamples && nbins <= 512 &&
                         num_rois * chunks < (1ll << 31);
+    if (!p.channels_last && workspace != nullptr && num_rois > 0) {
+        // NCHW input with a workspace from mb_roi_align_workspace_bytes: transpose once, gather channels-last
+        const size_t need = mb_roi_align_workspace_bytes(&p, num_rois);
+        if (need != 0 && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
+            char* w = (char*)workspace;
+            for (int l = 0; l < p.num_levels; ++l) {
+                const int HW = p.height[l] * p.width[l];
+                dim3 grid(ceil_div(HW, 32), ceil_div(p.channels, 32), p.num_images);
+                k_nchw_to_nhwc<<<grid, 256, 0, stream>>>(p.features[l], (float*)w, p.channels, HW);
+                MB_LAUNCH_CHECK();
+                p.features[l] = (const float*)w;
+                w += align_up((size_t)p.num_images * p.channels * HW * sizeof(float), 256);
+            }
+            p.channels_last = 1;
+        }
+    }
     if (p.channels_last) {
         if (!(p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)))
             return MB_ERR_UNSUPPORTED;   // the host converts to NCHW for other configurations

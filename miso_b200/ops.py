@@ -280,7 +280,7 @@ def convert_boxes_to_roi_format(boxes: Sequence[Tensor]) -> Tensor:
 
 def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence[float], thresholds: Sequence[float],
                       output_size: Tuple[int, int], sampling_ratio: int, aligned: bool, exact: bool,
-                      return_levels: bool = False):
+                      return_levels: bool = False, use_workspace: bool = True):
     lib = _lib.load()
     f0 = features[0]
     k = rois.shape[0]
@@ -308,7 +308,10 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
             p.features[i] = fc.data_ptr()
         for i, t in enumerate(thresholds):
             p.level_thresholds[i] = float(t)
-        rc = lib.mb_multiscale_roi_align(C.byref(p), _ptr(rois), k, _ptr(out), _ptr(levels), None, 0, _stream(f0))
+        ws_bytes = lib.mb_roi_align_workspace_bytes(C.byref(p), k) if use_workspace else 0
+        ws = _workspace(ws_bytes, f0.device) if ws_bytes else None
+        rc = lib.mb_multiscale_roi_align(C.byref(p), _ptr(rois), k, _ptr(out), _ptr(levels), _ptr(ws),
+                                         ws.numel() if ws is not None else 0, _stream(f0))
         _lib.check(rc, "mb_multiscale_roi_align")
     return (out, levels) if return_levels else out
 

@@ -133,6 +133,8 @@ class HotPath:
         self.rpn_ws = torch.empty((nb,), dtype=torch.uint8, device=dev)
         self.det_ws = torch.empty((db,), dtype=torch.uint8, device=dev)
         self._keep: List[Tensor] = []
+        self.roi_ws = None
+        self.features_layout = "nchw"
         self.kernel_launches_per_step = 7 + 1 + 7 + 2   # rpn(6 kernels + sweep), roi_align, det, crop
 
     # ------------------------------------------------------------------------------
@@ -143,12 +145,21 @@ class HotPath:
         outputs for the proposal slots; images: original uint8 HWC images."""
         self._keep = [*objectness, *deltas, *features, class_logits, box_regression, *images]
         for t in self._keep:
-            if t.device.type != "cuda" or not t.is_contiguous():
-                raise MisoB200Error("HotPath.bind: inputs must be contiguous CUDA tensors")
+            dense = t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+            if t.device.type != "cuda" or not dense:
+                raise MisoB200Error("HotPath.bind: inputs must be dense CUDA tensors")
         for l, (o, dl) in enumerate(zip(objectness, deltas)):
             self.rpn_params.objectness[l], self.rpn_params.deltas[l] = o.data_ptr(), dl.data_ptr()
+        # FPN maps: channels-last tensors (what a torch.channels_last backbone produces) are gathered in
+        # place; NCHW maps get a workspace so that the library can transpose them once per step
+        nhwc = all((not f.is_contiguous()) and f.is_contiguous(memory_format=torch.channels_last) for f in features)
+        self.roi_params.channels_last = int(nhwc)
         for l, f in enumerate(features):
             self.roi_params.features[l] = f.data_ptr()
+        nb = self.lib.mb_roi_align_workspace_bytes(C.byref(self.roi_params), self.s.num_images * self.R)
+        self.roi_ws = torch.empty((nb,), dtype=torch.uint8, device=self.dev) if nb else None
+        self.features_layout = "channels_last" if nhwc else "nchw"
+        self.kernel_launches_per_step = 7 + 1 + 7 + 2 + (len(features) if nb else 0)
         for i, im in enumerate(images):
             self.crop_params.images[i] = im.data_ptr()
         self.class_logits, self.box_regression = class_logits, box_regression
@@ -165,7 +176,8 @@ class HotPath:
     def roi_align(self, st=None):
         st = st or self._stream()
         _lib.check(self.lib.mb_multiscale_roi_align(C.byref(self.roi_params), _ptr(self.proposals),
-                                                    self.s.num_images * self.R, _ptr(self.box_features), None, None, 0, st),
+                                                    self.s.num_images * self.R, _ptr(self.box_features), None,
+                                                    _ptr(self.roi_ws), self.roi_ws.numel() if self.roi_ws is not None else 0, st),
                    "mb_multiscale_roi_align")
 
     def detections(self, st=None):

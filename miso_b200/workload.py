@@ -35,7 +35,8 @@ class Workload:
 
 def faster_rcnn_batch(num_images: int = 4, original: int = 1024, resized: int = 800, channels: int = 256,
                       num_classes: int = 3, post_nms_top_n: int = 1000, detections_per_img: int = 300,
-                      threshold: float = 0.5, seed: int = 0, pin: bool = True) -> Workload:
+                      threshold: float = 0.5, seed: int = 0, pin: bool = True,
+                      features_layout: str = "nchw") -> Workload:
     g = torch.Generator().manual_seed(seed)
     padded = -(-resized // 32) * 32
     grids = [(padded // s, padded // s) for s in (4, 8, 16, 32)]
@@ -43,14 +44,16 @@ def faster_rcnn_batch(num_images: int = 4, original: int = 1024, resized: int = 
     rpn_grids = grids + [pool]
     n = num_images
 
-    def rn(*shape, scale=1.0):
+    def rn(*shape, scale=1.0, channels_last=False):
         t = torch.randn(*shape, generator=g) * scale
+        if channels_last:   # same logical [N,C,H,W] tensor, NHWC strides (what a channels_last cuDNN backbone emits)
+            t = t.contiguous(memory_format=torch.channels_last)
         return t.pin_memory() if pin else t
 
     host = {
         "objectness": [rn(n, 3, gh, gw, scale=2.0) for gh, gw in rpn_grids],
         "deltas": [rn(n, 12, gh, gw, scale=0.5) for gh, gw in rpn_grids],
-        "features": [rn(n, channels, gh, gw) for gh, gw in grids],
+        "features": [rn(n, channels, gh, gw, channels_last=(features_layout == "channels_last")) for gh, gw in grids],
         "class_logits": [rn(n * post_nms_top_n, num_classes, scale=3.0)],
         "box_regression": [rn(n * post_nms_top_n, 4 * num_classes, scale=0.5)],
         "images": [],
@@ -64,9 +67,11 @@ def faster_rcnn_batch(num_images: int = 4, original: int = 1024, resized: int = 
     rpn = RpnConfig(RPN_SIZES, RPN_RATIOS, pre_nms_top_n=1000, post_nms_top_n=post_nms_top_n)
     det = DetConfig(detections_per_img=detections_per_img)
     name = (f"Faster R-CNN R50-FPN post-head path, batch {n}, {original}^2 images -> {resized}^2, "
-            f"{post_nms_top_n} RPN proposals/img, {channels} ch, RoIAlign 7x7, {detections_per_img} dets/img")
+            f"{post_nms_top_n} RPN proposals/img, {channels} ch ({features_layout} FPN maps), RoIAlign 7x7, "
+            f"{detections_per_img} dets/img")
     return Workload(name, shapes, rpn, det, threshold, host)
 
 
 def to_device(w: Workload, device) -> Dict[str, List[torch.Tensor]]:
+    # .to() keeps the memory format (channels_last stays channels_last)
     return {k: [t.to(device, non_blocking=True) for t in v] for k, v in w.host.items()}

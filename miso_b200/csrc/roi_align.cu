@@ -932,8 +932,8 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
-    const int opitch = (nbins & 1) ? nbins : nbins + 1;   // odd: rows (j*32 + lane) hit 32 distinct banks
-    float* ob = smem;                                                  // [4][32][opitch]: row j*32+lane = channel 4*lane+j
+    const int opitch = nbins | 1;                         // odd pitch: the rotated stores below are conflict-free
+    float* ob = smem;                                                  // [128][opitch]; == output layout when nbins is odd
     int4* tab_off = reinterpret_cast<int4*>(ob + ((kChunk4 * opitch + 3) & ~3));
     float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);
 
@@ -1001,19 +1001,30 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
                         a3 = fmaf(wv.x, v1.w, fmaf(wv.y, v2.w, fmaf(wv.z, v3.w, fmaf(wv.w, v4.w, a3))));
                     }
                 }
-                float* o = ob + lane * opitch + b;
-                o[0] = __fmul_rn(a0, 0.25f);
-                o[32 * opitch] = __fmul_rn(a1, 0.25f);
-                o[64 * opitch] = __fmul_rn(a2, 0.25f);
-                o[96 * opitch] = __fmul_rn(a3, 0.25f);
+                // Channel 4*lane+j goes to row 4*lane+j. Storing j in the order (lane/8 + t) % 4 spreads the
+                // four lanes that share (4*lane*nbins mod 32) over different j, i.e. over different banks.
+                a0 = __fmul_rn(a0, 0.25f); a1 = __fmul_rn(a1, 0.25f); a2 = __fmul_rn(a2, 0.25f); a3 = __fmul_rn(a3, 0.25f);
+                float* o = ob + (4 * lane) * opitch + b;
+                const int rot = lane >> 3;
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int j = (rot + t) & 3;
+                    const float v = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
+                    o[j * opitch] = v;
+                }
             }
         }
         __syncthreads();
-        // write out: channel c of the chunk sits in row (c % 4) * 32 + c / 4; 49 contiguous floats per channel
+        // write out: the chunk is one contiguous block of nch*nbins floats in the output
         float* dst = dst_roi + (size_t)c0 * nbins;
-        for (int ch = warp; ch < nch; ch += kRoiWarps) {
-            const float* src = ob + ((ch & 3) * 32 + (ch >> 2)) * opitch;
-            for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = src[b];
+        const int total = nch * nbins;
+        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(ob);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = tid; i < total / 4; i += kRoiThreads) d4[i] = s4[i];
+        } else {
+            for (int ch = warp; ch < nch; ch += kRoiWarps)
+                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
         }
         __syncthreads();   // ob is reused by the next chunk
     }
@@ -1140,7 +1151,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         bool aligned16 = true;
         for (int l = 0; l < p.num_levels; ++l) aligned16 = aligned16 && ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) == 0);
         if (vec && aligned16) {
-            const int smem4 = ((kChunk4 * opitch + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 32;
+            const int smem4 = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 32;
             if (p.exact) {
                 MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
                 k_roi_align_nhwc4<true><<<(int)num_rois, kRoiThreads, smem4, stream>>>(p, rois, out, levels_out);

@@ -1150,7 +1150,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const bool vec = (nv == nullptr || strcmp(nv, "scalar") != 0) && (p.channels % 4 == 0);
         bool aligned16 = true;
         for (int l = 0; l < p.num_levels; ++l) aligned16 = aligned16 && ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) == 0);
-        if (vec && aligned16) {
+        if (vec && aligned16 && nbins <= 64) {   // larger bins: the scalar variant keeps more CTAs resident
             const int smem4 = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 32;
             if (p.exact) {
                 MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));

@@ -280,6 +280,8 @@ def run_ours(args):
         if world > 1:
             torch.cuda.current_stream(dev).wait_event(ev_pack)
         hp.detections(st)
+        if roi_events is not None and len(roi_events) > 2:
+            roi_events[2].record()
         hp.crops(st)
 
     def step():
@@ -303,7 +305,7 @@ def run_ours(args):
         sampler.start()
     st = hp._stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    roi_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    roi_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
     ev0.record()
     for k in range(args.steps):
@@ -325,8 +327,12 @@ def run_ours(args):
         total_dets = float(dets_per_step)
     ms_per_step = ms / args.steps
     value = total_dets / (ms_per_step * 1e-3)
-    roi_ms = sorted(a.elapsed_time(b) for a, b in roi_ev)
+    roi_ms = sorted(e[0].elapsed_time(e[1]) for e in roi_ev)
     roi_mean_ms = sum(roi_ms) / len(roi_ms)
+    det_mean_ms = sum(e[1].elapsed_time(e[2]) for e in roi_ev) / len(roi_ev)
+    # RPN and crop stages: from each step's crop-start event to the next step's RoIAlign-start event
+    tail_ms = [roi_ev[i][2].elapsed_time(roi_ev[i + 1][0]) for i in range(len(roi_ev) - 1)]
+    tail_mean_ms = sum(tail_ms) / max(len(tail_ms), 1)
 
     # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step ----
     host_out = {k: torch.empty_like(getattr(hp, k), device="cpu").pin_memory()
@@ -404,6 +410,7 @@ def run_ours(args):
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
                      "kernel_share_of_step": roi_mean_ms / ms_per_step},
+        "stage_ms": {"roi_align": roi_mean_ms, "det_postprocess": det_mean_ms, "crop_then_next_rpn": tail_mean_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps},
         "gpu_launches": hp.kernel_launches_per_step * args.steps,

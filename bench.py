@@ -28,7 +28,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -62,30 +61,30 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region, sampled through NVML every ~2 ms
-    (the region is only tens of milliseconds long; nvidia-smi would yield a single sample)."""
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region, read through NVML from the launching
+    thread between steps (the region lasts tens of milliseconds; the host runs ahead of the GPU, so
+    the reads do not stall it)."""
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
-        self.max_mhz = None
-
-    def run(self):
+        self.rows, self.max_mhz, self.h, self.nv = [], None, None, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            while not self._halt.is_set():
-                self.rows.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h)))
-                self._halt.wait(0.002)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            pass
+            self.nv = None
 
-    def stop(self):
-        self._halt.set()
-        self.join(timeout=5)
+    def sample(self):
+        if self.nv is not None:
+            try:
+                self.rows.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM),
+                                  self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
+            except Exception:
+                pass
+
+    def summary(self):
         sm = sorted(r[0] for r in self.rows)
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
         reasons = sorted({n for _, m in self.rows for n, b in bits.items() if m & b})
@@ -301,8 +300,6 @@ def run_ours(args):
 
     # ---- timed region: K steps, device timed, RoIAlign launches individually bracketed ----
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     st = hp._stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     roi_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
@@ -312,11 +309,13 @@ def run_ours(args):
         hot_path(st, roi_ev[k])
         if world > 1:
             exchange_and_seam()
+        if rank == 0 and (k & 3) == 3:
+            sampler.sample()                     # the GPU is still working through the queued steps
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(comm)     # the timed region ends with the last seam NMS
     ev1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.summary() if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms, float(dets_per_step)], dtype=torch.float64, device=dev)
     if world > 1:

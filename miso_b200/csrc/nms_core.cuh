@@ -510,20 +510,27 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegA
         const int nb = min(64, n - b * 64);
         const unsigned long long* tile = rowsm + (size_t)(b * 64) * T + b;   // word(t, col) = tile[t*T + col]
         if (warp == 0) {
+            // Greedy resolve of the block. supp(t) = earlier boxes of the block that overlap box t (lower
+            // bits of its diagonal word); t is kept iff it is not removed from outside and no kept earlier
+            // box overlaps it. The loads do not depend on the chain, so the 64 steps cost ~4 dependent
+            // ALU operations each; every lane runs the same chain (no divergence, no exchange).
             const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
-            unsigned long long R = removed[b] | invalid, C = 0;
-            const int t0 = lane, t1 = lane + 32;
-            const unsigned long long s0 = (t0 < nb) ? (tile[t0 * T] & ((1ull << t0) - 1ull)) : 0ull;
-            const unsigned long long s1 = (t1 < nb) ? (tile[t1 * T] & ((1ull << t1) - 1ull)) : 0ull;
-            while ((C | R) != ~0ull) {
-                const unsigned long long D = C | R;
-                bool c0 = false, r0 = false, c1 = false, r1 = false;
-                if (!((D >> t0) & 1ull)) { if (s0 & C) r0 = true; else if ((s0 & ~R) == 0ull) c0 = true; }
-                if (!((D >> t1) & 1ull)) { if (s1 & C) r1 = true; else if ((s1 & ~R) == 0ull) c1 = true; }
-                C |= (unsigned long long)__ballot_sync(0xffffffffu, c0) | ((unsigned long long)__ballot_sync(0xffffffffu, c1) << 32);
-                R |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+            const unsigned long long dead = removed[b] | invalid;
+            unsigned int klo = 0, khi = 0;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const unsigned int slo = (t < nb) ? (unsigned int)tile[t * T] : 0u;   // only earlier bits matter
+                const bool k = !((dead >> t) & 1ull) && ((slo & klo & ((1u << t) - 1u)) == 0u);
+                klo |= k ? (1u << t) : 0u;
             }
-            unsigned long long keepw = C;
+#pragma unroll
+            for (int t = 32; t < 64; ++t) {
+                const unsigned long long sw = (t < nb) ? tile[t * T] : 0ull;
+                const unsigned int slo = (unsigned int)sw, shi = (unsigned int)(sw >> 32);
+                const bool k = !((dead >> t) & 1ull) && (((slo & klo) | (shi & khi & ((1u << (t - 32)) - 1u))) == 0u);
+                khi |= k ? (1u << (t - 32)) : 0u;
+            }
+            unsigned long long keepw = ((unsigned long long)khi << 32) | klo;
             if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
                 int extra = kept + __popcll(keepw) - max_keep;
                 while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
@@ -537,17 +544,21 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegA
             for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
             break;
         }
-        {
+        {   // removed[b + col] |= OR of the kept rows' words: 4 adjacent lanes share a column (a quarter of the
+            // rows each), combine with two shuffles, and one of them owns the update (no atomics)
             const int Wn = T - b;
             const int col = 1 + (tid >> 2), q = tid & 3;
+            unsigned long long acc = 0;
             if (col < Wn) {
-                unsigned long long acc = 0, bits = (keepw >> (16 * q)) & 0xffffull;
+                unsigned long long bits = (keepw >> (16 * q)) & 0xffffull;
                 while (bits) {
                     const int t = __ffsll((long long)bits) - 1 + 16 * q; bits &= bits - 1;
                     acc |= tile[t * T + col];
                 }
-                if (acc) atomicOr(&removed[b + col], acc);
             }
+            acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && col < Wn && acc) removed[b + col] |= acc;
         }
         __syncthreads();
     }

@@ -61,35 +61,58 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as nv
+nv.nvmlInit()
+h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+print("max", nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM), flush=True)
+while True:
+    print(time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksEventReasons(h), flush=True)
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, read through NVML from the launching
-    thread between steps (the region lasts tens of milliseconds; the host runs ahead of the GPU, so
-    the reads do not stall it)."""
+    """SM clock and throttle reasons DURING the timed region: a helper process polls NVML every ~1 ms
+    (its own interpreter, so it neither holds this process's GIL nor delays the launch loop); only the
+    samples stamped inside [t0, t1] are kept."""
 
     def __init__(self, index: int):
-        self.rows, self.max_mhz, self.h, self.nv = [], None, None, None
+        import tempfile
+        self.out = tempfile.TemporaryFile(mode="w+")
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(index)], stdout=self.out,
+                                         stderr=subprocess.DEVNULL)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def sample(self):
-        if self.nv is not None:
-            try:
-                self.rows.append((self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM),
-                                  self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)))
-            except Exception:
-                pass
-
-    def summary(self):
-        sm = sorted(r[0] for r in self.rows)
+    def summary(self, t0: float, t1: float):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.out.seek(0)
+        mx, rows, before = None, [], None
+        for line in self.out.read().splitlines():
+            f = line.split()
+            if len(f) == 2 and f[0] == "max":
+                mx = int(f[1])
+            elif len(f) == 3:
+                ts, mhz, mask = float(f[0]), int(f[1]), int(f[2])
+                if t0 <= ts <= t1:
+                    rows.append((mhz, mask))
+                elif ts < t0:
+                    before = (mhz, mask)
+        if not rows and before is not None:
+            rows = [before]
+        sm = sorted(r[0] for r in rows)
         bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
-        reasons = sorted({n for _, m in self.rows for n, b in bits.items() if m & b})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = sorted({n for _, m in rows for n, b in bits.items() if m & b})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons, "samples": len(rows)}
 
 
 def roi_align_algorithmic_bytes(proposals, counts, shapes, thresholds, scales, channels, pooled, sr=2):
@@ -245,6 +268,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # started early: it must be polling before the timed region
     w = workload.faster_rcnn_batch(num_images=args.batch, seed=rank, features_layout=args.features_layout)
     hp = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=512 << 20,
                           exact_roi_align=not args.fast_roi_align, device=dev)
@@ -299,23 +323,21 @@ def run_ours(args):
     crop_bytes = tot[1]
 
     # ---- timed region: K steps, device timed, RoIAlign launches individually bracketed ----
-    sampler = ClockSampler(local)
     st = hp._stream()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     roi_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
+    wall0 = time.time()
     ev0.record()
     for k in range(args.steps):
         hot_path(st, roi_ev[k])
         if world > 1:
             exchange_and_seam()
-        if rank == 0 and (k & 3) == 3:
-            sampler.sample()                     # the GPU is still working through the queued steps
     if world > 1:
         torch.cuda.current_stream(dev).wait_stream(comm)     # the timed region ends with the last seam NMS
     ev1.record()
     barrier()
-    clocks = sampler.summary() if rank == 0 else None
+    clocks = sampler.summary(wall0, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms, float(dets_per_step)], dtype=torch.float64, device=dev)
     if world > 1:

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--fast-roi-align", action="store_true", help="FMA RoIAlign (<=1e-5) instead of the bit-exact order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one batch at a time on one stream (no cross-batch overlap)")
     ap.add_argument("--features-layout", default="channels_last", choices=["channels_last", "nchw"],
                     help="memory format of the synthetic FPN maps: channels_last = what a torch.channels_last "
                          "cuDNN backbone produces (gathered in place); nchw = the reference's default layout")
@@ -279,63 +280,92 @@ def run_ours(args):
     origins = torch.tensor([[rank * 896.0, i * 896.0] for i in range(n)], dtype=torch.float32, device=dev)
     seam = mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev) if world > 1 else None
 
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    ev_det, ev_pack = torch.cuda.Event(), torch.cuda.Event()
+    # Three batches in flight (pipeline.OverlappedHotPath): the RPN stage of batch k+2 and the detection/crop
+    # stages of batch k are chains of few-CTA kernels that run beside batch k+1's RoIAlign. Every batch still
+    # runs rpn -> roi_align -> detections -> crops in the reference's order (event-chained).
+    slots = 1 if args.serial else 3
+    hps = [hp]
+    for _ in range(slots - 1):
+        h2 = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=64 << 20,
+                              exact_roi_align=not args.fast_roi_align, device=dev)
+        h2.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
+        hps.append(h2)
+    plan = pipeline.OverlappedHotPath(hps)
 
-    def exchange_and_seam():
-        """The path's one exchange, on its own stream so that it overlaps the next batch's hot path:
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    ev_det = [torch.cuda.Event() for _ in hps]
+    ev_pack = [None for _ in hps]
+    roi_ev = []           # (start, end) CUDA events around every RoIAlign launch of the timed region, on its stream
+
+    def before_roi(i, hp_i, st):
+        if roi_ev is not None and recording[0]:
+            e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            roi_ev.append(e)
+            e[0].record(st)
+
+    def after_roi(i, hp_i, st):
+        if recording[0]:
+            roi_ev[-1][1].record(st)
+
+    def before_det(i, hp_i, st):
+        if world > 1 and ev_pack[i] is not None:
+            st.wait_event(ev_pack[i])        # the previous exchange has read this slot's detection buffers
+
+    def after_det(i, hp_i, st):
+        """The path's one exchange, on its own stream so that it overlaps the following batches:
         fixed-size blocks -> one all_gather_into_tensor -> seam NMS right behind it, no host sync."""
-        ev_det.record()
+        if world == 1:
+            return
+        ev_det[i].record(st)
         with torch.cuda.stream(comm):
-            comm.wait_event(ev_det)
-            block = mosaic.pack_block(hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts, origins, w.threshold, n * dpi)
-            ev_pack.record(comm)                 # the detection buffers may be overwritten from here on
+            comm.wait_event(ev_det[i])
+            block = mosaic.pack_block(hp_i.det_boxes, hp_i.det_scores, hp_i.det_labels, hp_i.det_counts, origins,
+                                      w.threshold, n * dpi)
+            ev_pack[i] = torch.cuda.Event(); ev_pack[i].record(comm)
             seam.launch(mosaic.exchange(block, world), w.det.nms_thresh)
 
-    def hot_path(st=None, roi_events=None):
-        st = st or hp._stream()
-        hp.rpn(st)
-        if roi_events is not None:
-            roi_events[0].record()
-        hp.roi_align(st)
-        if roi_events is not None:
-            roi_events[1].record()
-        if world > 1:
-            torch.cuda.current_stream(dev).wait_event(ev_pack)
-        hp.detections(st)
-        if roi_events is not None and len(roi_events) > 2:
-            roi_events[2].record()
-        hp.crops(st)
+    recording = [False]
+    plan.hooks.update(before_roi=before_roi, after_roi=after_roi, before_det=before_det, after_det=after_det)
 
-    def step():
-        hot_path()
-        if world > 1:
-            exchange_and_seam()
-        return None
+    host_enqueue = [0.0]
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def run_steps(k):
+        t_h = time.perf_counter()
+        for _ in range(k):
+            plan.submit()
+        host_enqueue[0] = (time.perf_counter() - t_h) / k
+        plan.drain()
+        if world > 1:
+            torch.cuda.current_stream(dev).wait_stream(comm)     # the region ends with the last seam NMS
+
+    run_steps(max(args.warmup, 3))
     barrier()
     tot = hp.crop_totals.tolist()
     if tot[2]:
         raise SystemExit("crop buffer overflow")
     dets_per_step = tot[0]
     crop_bytes = tot[1]
+    for h2 in hps[1:]:
+        assert h2.crop_totals.tolist() == tot
 
-    # ---- timed region: K steps, device timed, RoIAlign launches individually bracketed ----
-    st = hp._stream()
+    # ---- stage breakdown from a short serial pass (one batch at a time on one stream; not the timed region) ----
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(5)]
+    for es in sev:
+        es[0].record(); hp.rpn(); es[1].record(); hp.roi_align(); es[2].record(); hp.detections(); es[3].record()
+        hp.crops(); es[4].record()
+    barrier()
+    names = ("rpn", "roi_align", "det_postprocess", "filter_crop")
+    serial_stage_ms = {nm: sorted(es[j].elapsed_time(es[j + 1]) for es in sev)[len(sev) // 2] for j, nm in enumerate(names)}
+
+    # ---- timed region: K steps (K batches submitted and completed), device timed; RoIAlign launches bracketed ----
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    roi_ev = [tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(args.steps)]
     barrier()
     wall0 = time.time()
+    recording[0] = True
     ev0.record()
-    for k in range(args.steps):
-        hot_path(st, roi_ev[k])
-        if world > 1:
-            exchange_and_seam()
-    if world > 1:
-        torch.cuda.current_stream(dev).wait_stream(comm)     # the timed region ends with the last seam NMS
+    run_steps(args.steps)
     ev1.record()
+    recording[0] = False
     barrier()
     clocks = sampler.summary(wall0, time.time()) if rank == 0 else None
     ms = ev0.elapsed_time(ev1)
@@ -350,43 +380,47 @@ def run_ours(args):
     value = total_dets / (ms_per_step * 1e-3)
     roi_ms = sorted(e[0].elapsed_time(e[1]) for e in roi_ev)
     roi_mean_ms = sum(roi_ms) / len(roi_ms)
-    det_mean_ms = sum(e[1].elapsed_time(e[2]) for e in roi_ev) / len(roi_ev)
-    # RPN and crop stages: from each step's crop-start event to the next step's RoIAlign-start event
-    tail_ms = [roi_ev[i][2].elapsed_time(roi_ev[i + 1][0]) for i in range(len(roi_ev) - 1)]
-    tail_mean_ms = sum(tail_ms) / max(len(tail_ms), 1)
 
-    # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step ----
-    host_out = {k: torch.empty_like(getattr(hp, k), device="cpu").pin_memory()
-                for k in ("det_boxes", "det_scores", "det_labels", "det_counts", "crop_rects", "crop_xywh", "crop_src",
-                          "crop_offsets", "crop_totals")}
-    host_pix = torch.empty((hp.crop_capacity,), dtype=torch.uint8).pin_memory()
-    dev_lists = {k: d[k] for k in w.host}
+    # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step, through the public host-facing
+    # API (pipeline.HostPipeline: copy-in / compute / copy-out streams, two slots) ----
+    seams = {}
 
-    def e2e_step():
-        for k, hs in w.host.items():
-            for src, dst in zip(hs, dev_lists[k]):
-                dst.copy_(src, non_blocking=True)
-        hot_path()
-        for k, ht in host_out.items():
-            ht.copy_(getattr(hp, k), non_blocking=True)
-        torch.cuda.synchronize()
-        nb = int(host_out["crop_totals"][1])
-        host_pix[:nb].copy_(hp.crop_pixels[:nb], non_blocking=True)
-        if world > 1:
-            exchange_and_seam()
-            comm.synchronize()
-            b, s, l = seam.finish()
-            b.cpu()
-        torch.cuda.synchronize()
-        return nb
+    def make_hp():
+        return pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=128 << 20,
+                                exact_roi_align=not args.fast_roi_align, device=dev)
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    def on_computed(hp_s, slot):
+        if world == 1:
+            return
+        sm_ = seams.setdefault(id(slot), mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev))
+        block = mosaic.pack_block(hp_s.det_boxes, hp_s.det_scores, hp_s.det_labels, hp_s.det_counts, origins, w.threshold, n * dpi)
+        sm_.launch(mosaic.exchange(block, world), w.det.nms_thresh)
+        slot["seam_done"] = torch.cuda.Event(); slot["seam_done"].record()
+
+    def on_collect(hp_s, slot):
+        if world == 1:
+            return None
+        slot["seam_done"].synchronize()
+        b, s_, l = seams[id(slot)].finish()
+        return b.cpu(), s_.cpu(), l.cpu()
+
+    pipe = pipeline.HostPipeline(make_hp, w.host, depth=2, on_computed=on_computed, on_collect=on_collect)
+    d2h_small = sum(t_.numel() * t_.element_size() for t_ in pipe.slots[0]["out"].values())
+
+    def e2e_run(k):
+        got = 0
+        for _ in range(k):
+            r = pipe.submit(w.host)
+            got += r is not None
+        got += len(pipe.flush())
+        assert got == k
+        return r
+
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        nb = e2e_step()
+    e2e_run(e2e_steps)          # every batch: H2D of all inputs, the path, D2H of detections + crops; drained at the end
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -394,7 +428,7 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total_dets / float(te[0])
     h2d = w.input_bytes()
-    d2h = sum(t_.numel() * t_.element_size() for t_ in host_out.values()) + crop_bytes
+    d2h = d2h_small + crop_bytes
 
     if rank != 0:
         if world > 1:
@@ -426,14 +460,18 @@ def run_ours(args):
         "config": {"workload": w.name, "per_gpu_batch": args.batch, "features_layout": hp.features_layout, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
                    "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step on a second stream (overlaps the next batch)" if world > 1 else "single GPU",
-                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
+                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes,
+                   "batches_in_flight": slots,
+                   "overlap": ("3 batches in flight on 3 streams: rpn(k+2) | roi_align(k+1) | detections+crops(k); "
+                               "per-batch stage order kept by events") if slots > 1 else "none (serial)"},
         "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
                      "kernel_share_of_step": roi_mean_ms / ms_per_step},
-        "stage_ms": {"roi_align": roi_mean_ms, "det_postprocess": det_mean_ms, "crop_then_next_rpn": tail_mean_ms},
+        "serial_stage_ms": serial_stage_ms, "host_enqueue_ms_per_step": 1e3 * host_enqueue[0],
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps},
+                "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps,
+                "api": "miso_b200.pipeline.HostPipeline (pinned host in/out, copy-in | compute | copy-out streams, 2 batches in flight)"},
         "gpu_launches": hp.kernel_launches_per_step * args.steps,
         "clocks": clocks,
     }

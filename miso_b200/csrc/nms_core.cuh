@@ -15,6 +15,7 @@
 //   sweep   : one CTA per segment; serial 64-step resolve of the diagonal word, parallel OR
 //             of the kept rows into the removed[] bit-vector held in shared memory
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 namespace mb {
@@ -484,23 +485,25 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegA
     unsigned long long* kb = keepbits + s.keep_off[g];
     if (tid < T) removed[tid] = 0;
     {   // rows are T words; only words >= the row's own block were written by the mask kernel.
-        // 8 independent loads are issued before the first store (memory-level parallelism).
-        const int total = n * T;
-        for (int base = 0; base < total; base += 8 * kSweepThreads) {
-            unsigned long long v[8];
+        // Thread = (column, row mod rows_per_pass) with the column count padded to a power of two (no
+        // division); 8 independent loads are issued before the first store (memory-level parallelism).
+        int lg = 0;
+        while ((1 << lg) < T) ++lg;
+        const int col = tid & ((1 << lg) - 1), r0 = tid >> lg, rstep = kSweepThreads >> lg;
+        if (col < T) {
+            for (int base = r0; base < n; base += 8 * rstep) {
+                unsigned long long v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = base + u * kSweepThreads + tid;
-                v[u] = 0;
-                if (idx < total) {
-                    const int row = idx / T, col = idx - row * T;
-                    if (col >= (row >> 6)) v[u] = __ldg(m + idx);
+                for (int u = 0; u < 8; ++u) {
+                    const int row = base + u * rstep;
+                    v[u] = 0;
+                    if (row < n && col >= (row >> 6)) v[u] = __ldg(m + (size_t)row * T + col);
                 }
-            }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int idx = base + u * kSweepThreads + tid;
-                if (idx < total) rowsm[idx] = v[u];
+                for (int u = 0; u < 8; ++u) {
+                    const int row = base + u * rstep;
+                    if (row < n) rowsm[row * T + col] = v[u];
+                }
             }
         }
     }
@@ -520,14 +523,14 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegA
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const unsigned int slo = (t < nb) ? (unsigned int)tile[t * T] : 0u;   // only earlier bits matter
-                const bool k = !((dead >> t) & 1ull) && ((slo & klo & ((1u << t) - 1u)) == 0u);
+                const bool k = !((dead >> t) & 1ull) && ((slo & klo) == 0u);   // klo holds bits < t only
                 klo |= k ? (1u << t) : 0u;
             }
 #pragma unroll
             for (int t = 32; t < 64; ++t) {
                 const unsigned long long sw = (t < nb) ? tile[t * T] : 0ull;
                 const unsigned int slo = (unsigned int)sw, shi = (unsigned int)(sw >> 32);
-                const bool k = !((dead >> t) & 1ull) && (((slo & klo) | (shi & khi & ((1u << (t - 32)) - 1u))) == 0u);
+                const bool k = !((dead >> t) & 1ull) && (((slo & klo) | (shi & khi)) == 0u);   // khi holds bits < t only
                 khi |= k ? (1u << (t - 32)) : 0u;
             }
             unsigned long long keepw = ((unsigned long long)khi << 32) | klo;
@@ -575,7 +578,10 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
     const long long pre_bytes = (long long)max_seg_elems * ceil_div(max_seg_elems, 64) * 8;
-    if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords && pre_bytes <= 160 * 1024) {
+    // the whole-mask preload variant needs up to 160 KB of shared memory per CTA; measured slightly slower than the
+    // tile-at-a-time sweep and it cannot co-reside with RoIAlign CTAs of another stream, so it is opt-in (MB_SWEEP=p)
+    static const bool preload = [] { const char* e = getenv("MB_SWEEP"); return e && e[0] == 'p'; }();
+    if (preload && ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords && pre_bytes <= 160 * 1024) {
         MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_preload, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_bytes));
         k_nms_sweep_preload<<<G, kSweepThreads, (int)pre_bytes, stream>>>(s, mask, keepbits, max_keep);
         MB_LAUNCH_CHECK();

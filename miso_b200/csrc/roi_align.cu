@@ -918,6 +918,14 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_nhwc(const mb_roi_
     }
 }
 
+// Rotate (a0..a3) so that element t of the result is a[(rot + t) & 3]: two select stages instead of a
+// select chain per element. Lane groups of 8 use different rotations, which spreads the four lanes
+// that share a bank (row pitch odd, 4 rows per lane) over four banks.
+__device__ __forceinline__ void rotate4(float4& a, int rot) {
+    if (rot & 1) { const float t = a.x; a.x = a.y; a.y = a.z; a.z = a.w; a.w = t; }
+    if (rot & 2) { float t = a.x; a.x = a.z; a.z = t; t = a.y; a.y = a.w; a.w = t; }
+}
+
 // Channels-last, 16-byte gathers: lane = 4 consecutive channels, a warp covers 128 channels per tap
 // (four 128-byte lines). Table loads, address arithmetic and loop overhead are amortised over 4x
 // the outputs of the scalar variant. Needs C % 4 == 0 and 16-byte aligned maps.
@@ -967,6 +975,10 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
     }
     __syncthreads();
     const char* img = reinterpret_cast<const char*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C * 4;
+    const int rot4 = lane >> 3;
+    int so4[4];                                                        // smem row offsets in rotated order
+#pragma unroll
+    for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * opitch;
     const int nchunks = (C + kChunk4 - 1) / kChunk4;
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int c0 = chunk * kChunk4;
@@ -1004,14 +1016,10 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
                 // Channel 4*lane+j goes to row 4*lane+j. Storing j in the order (lane/8 + t) % 4 spreads the
                 // four lanes that share (4*lane*nbins mod 32) over different j, i.e. over different banks.
                 a0 = __fmul_rn(a0, 0.25f); a1 = __fmul_rn(a1, 0.25f); a2 = __fmul_rn(a2, 0.25f); a3 = __fmul_rn(a3, 0.25f);
+                float4 av = make_float4(a0, a1, a2, a3);
+                rotate4(av, rot4);
                 float* o = ob + (4 * lane) * opitch + b;
-                const int rot = lane >> 3;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int j = (rot + t) & 3;
-                    const float v = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
-                    o[j * opitch] = v;
-                }
+                o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
             }
         }
         __syncthreads();
@@ -1027,6 +1035,165 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
                 for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
         }
         __syncthreads();   // ob is reused by the next chunk
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Channels-last, separable merged-tap gather (the `exact = 0` mode; results within 1e-5 of the
+// reference, not bit-identical). The sample grid of a RoI is a tensor product, so a bin is
+//     out[ph][pw] = 1/count * sum_y Wy[ph][y] * ( sum_x Wx[pw][x] * F[y][x] )
+// where Wy[ph] has at most four non-zero rows (two samples x two taps) and usually three, because
+// at the pyramid level the LevelMapper picks a RoI is 14..28 pixels across, the half-bin sample
+// spacing is 1..2 pixels and the two samples of a bin share a pixel row (column). Taps that fall on
+// the same row / column are merged when the per-RoI tables are built, zero-weight slots are skipped,
+// and a row that closes bin ph and opens bin ph+1 is summed once. A work item is (pw, 4 channels):
+// it walks the rows top to bottom, loads every (row, column) it needs once as one 16-byte vector
+// (consecutive lanes = consecutive channels: 512-byte coalesced), and produces the PH outputs of its
+// column. Per 4 channels that is ~7 x 17 x 3 = 360 vector loads per RoI instead of 784 — this kernel
+// is bound by L1 wavefronts, so that is where the time goes. Outputs are staged in shared memory
+// ([channel][odd pitch], rotated stores) and leave as one contiguous coalesced block.
+// ------------------------------------------------------------------------------------------
+constexpr int kSepThreads = 448;   // 7 pooled columns x 64 channel vectors (256 channels)
+
+// Merge the four taps of one pooled bin along one axis (two samples x {lo, hi}) into distinct pixel
+// indices with summed weights, compacted to the front; returns how many are left (0..4).
+__device__ __forceinline__ int merge_axis_slots(const Tap& A, const Tap& B, int r[4], float w[4]) {
+    int rr[4] = {A.lo, A.hi, B.lo, B.hi};
+    float ww[4] = {A.h, A.l, B.h, B.l};                // make_tap zeroes the weights of an out-of-range sample
+    if (rr[1] == rr[0]) { ww[0] += ww[1]; ww[1] = 0.f; }
+    if (rr[3] == rr[2]) { ww[2] += ww[3]; ww[3] = 0.f; }
+    if (rr[2] == rr[0]) { ww[0] += ww[2]; ww[2] = 0.f; } else if (rr[2] == rr[1]) { ww[1] += ww[2]; ww[2] = 0.f; }
+    if (rr[3] == rr[0]) { ww[0] += ww[3]; ww[3] = 0.f; } else if (rr[3] == rr[1]) { ww[1] += ww[3]; ww[3] = 0.f; }
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { r[j] = 0; w[j] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (ww[j] != 0.f) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) if (t == n) { r[t] = rr[j]; w[t] = ww[j]; }
+            ++n;
+        }
+    return n;
+}
+
+// R = sum over the NX merged columns of one pixel row (all loads issued before the first use)
+template <int NX>
+__device__ __forceinline__ float4 sep_row_sum(const float4* __restrict__ rp, const unsigned (&xo)[4], const float (&xw)[4]) {
+    float4 v[NX > 0 ? NX : 1];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) v[i] = __ldg(rp + xo[i]);
+    float4 R = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+        R.x = fmaf(xw[i], v[i].x, R.x); R.y = fmaf(xw[i], v[i].y, R.y);
+        R.z = fmaf(xw[i], v[i].z, R.z); R.w = fmaf(xw[i], v[i].w, R.w);
+    }
+    return R;
+}
+
+__global__ void __maxnreg__(48) k_roi_align_nhwc_sep(const mb_roi_align_params p,
+                                                                     const float* __restrict__ rois,
+                                                                     float* __restrict__ out, int* __restrict__ levels_out,
+                                                                     int chunk_c) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ unsigned s_yoff[64], s_xoff[64];   // [bin index along the axis][4 slots], units of 16 bytes
+    __shared__ float s_yw[64], s_xw[64];
+    __shared__ int s_ny[16], s_nx[16];
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
+    const int opitch = nbins | 1;
+    float* ob = smem;                                                  // [chunk_c][opitch]
+
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);
+    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
+    const int C = p.channels, C4 = C >> 2;
+    float* dst_roi = out + (size_t)k * C * nbins;
+    if (g.batch < 0 || g.batch >= p.num_images) {
+        for (long long i = tid; i < (long long)C * nbins; i += blockDim.x) dst_roi[i] = 0.0f;
+        return;
+    }
+    if (tid < PH) {
+        const Tap A = make_tap(g.start_h, g.bin_h, tid, 0, 2, g.H), B = make_tap(g.start_h, g.bin_h, tid, 1, 2, g.H);
+        int rr[4]; float ww[4];
+        s_ny[tid] = merge_axis_slots(A, B, rr, ww);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            s_yoff[tid * 4 + j] = (unsigned)rr[j] * (unsigned)g.W * (unsigned)C4;
+            s_yw[tid * 4 + j] = ww[j] * 0.25f;                         // 1/count folded in (count = 4, exact scaling)
+        }
+    } else if (tid >= 32 && tid < 32 + PW) {
+        const int t = tid - 32;
+        const Tap A = make_tap(g.start_w, g.bin_w, t, 0, 2, g.W), B = make_tap(g.start_w, g.bin_w, t, 1, 2, g.W);
+        int rr[4]; float ww[4];
+        s_nx[t] = merge_axis_slots(A, B, rr, ww);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_xoff[t * 4 + j] = (unsigned)rr[j] * (unsigned)C4; s_xw[t * 4 + j] = ww[j]; }
+    }
+    __syncthreads();
+    const float4* img = reinterpret_cast<const float4*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C4;
+    const int chunk4 = chunk_c >> 2;
+    const int rot = lane >> 3;
+    int so[4];                                                         // smem row offsets in rotated order
+#pragma unroll
+    for (int t = 0; t < 4; ++t) so[t] = ((rot + t) & 3) * opitch;
+    for (int c0 = 0; c0 < C; c0 += chunk_c) {
+        const int n4 = min(chunk4, (C - c0) >> 2);
+        const int items = PW * n4;
+        const float inv_n4 = 1.0f / (float)n4;
+        for (int it = tid; it < items; it += blockDim.x) {
+            int pw = (int)((float)it * inv_n4);
+            if ((pw + 1) * n4 <= it) ++pw;
+            if (pw * n4 > it) --pw;
+            const int c4 = it - pw * n4;
+            const float4* gp = img + (c0 >> 2) + c4;
+            unsigned xo[4]; float xw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { xo[i] = s_xoff[pw * 4 + i]; xw[i] = s_xw[pw * 4 + i]; }
+            const int nx = s_nx[pw];
+            unsigned prev = 0xffffffffu;
+            float4 R = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* o = ob + (4 * c4) * opitch + pw;
+            for (int ph = 0; ph < PH; ++ph) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ny = s_ny[ph];
+                for (int j = 0; j < ny; ++j) {
+                    const unsigned yo = s_yoff[ph * 4 + j];
+                    const float wy = s_yw[ph * 4 + j];
+                    if (yo != prev) {                                  // a row shared with the previous bin is summed once
+                        prev = yo;
+                        const float4* rp = gp + yo;
+                        if (nx == 3) R = sep_row_sum<3>(rp, xo, xw);
+                        else if (nx == 2) R = sep_row_sum<2>(rp, xo, xw);
+                        else if (nx == 4) R = sep_row_sum<4>(rp, xo, xw);
+                        else if (nx == 1) R = sep_row_sum<1>(rp, xo, xw);
+                        else R = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    acc.x = fmaf(wy, R.x, acc.x); acc.y = fmaf(wy, R.y, acc.y);
+                    acc.z = fmaf(wy, R.z, acc.z); acc.w = fmaf(wy, R.w, acc.w);
+                }
+                rotate4(acc, rot);
+                float* ob_bin = o + ph * PW;
+                ob_bin[so[0]] = acc.x; ob_bin[so[1]] = acc.y; ob_bin[so[2]] = acc.z; ob_bin[so[3]] = acc.w;
+            }
+        }
+        __syncthreads();
+        float* dst = dst_roi + (size_t)c0 * nbins;
+        const int total = 4 * n4 * nbins;
+        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(ob);
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = tid; i < total / 4; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            const int nw = blockDim.x >> 5, warp = tid >> 5;
+            for (int ch = warp; ch < 4 * n4; ch += nw)
+                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
+        }
+        __syncthreads();
     }
 }
 
@@ -1150,6 +1317,22 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const bool vec = (nv == nullptr || strcmp(nv, "scalar") != 0) && (p.channels % 4 == 0);
         bool aligned16 = true;
         for (int l = 0; l < p.num_levels; ++l) aligned16 = aligned16 && ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) == 0);
+        const char* sp = getenv("MB_ROI_SEP");
+        if (!p.exact && vec && aligned16 && sp != nullptr && sp[0] == '1') {   // experimental, measured slower than nhwc4
+            // separable merged-tap kernel (fast mode): channel chunk sized so that the staged outputs stay <= ~50 KB
+            int chunk_c = ((52 * 1024) / ((nbins | 1) * (int)sizeof(float))) & ~3;
+            if (chunk_c > p.channels) chunk_c = p.channels;
+            if (chunk_c >= 128) chunk_c &= ~127;                      // whole warps share one pooled column
+            if (chunk_c >= 4) {
+                const int items = p.pooled_w * (chunk_c / 4);
+                const int threads = min(kSepThreads, (items + 31) & ~31);
+                const int smem = chunk_c * (nbins | 1) * (int)sizeof(float);
+                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+                k_roi_align_nhwc_sep<<<(int)num_rois, threads, smem, stream>>>(p, rois, out, levels_out, chunk_c);
+                MB_LAUNCH_CHECK();
+                return MB_OK;
+            }
+        }
         if (vec && aligned16 && nbins <= 64) {   // larger bins: the scalar variant keeps more CTAs resident
             const int smem4 = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 32;
             if (p.exact) {

@@ -225,3 +225,176 @@ class HotPath:
             out[int(src[j]) // self.dpi].append({"xywh": xywh[j], "label": int(labels[src[j]]),
                                                 "score": float(scores[src[j]]), "crop": arr})
         return out
+
+
+class HostPipeline:
+    """Host-facing driver of the hot path: inputs arrive in pinned host memory, results leave in
+    pinned host memory, and the three legs of a batch run on three streams so that batch i+1's
+    host->device copy, batch i's kernels and batch i-1's device->host read overlap:
+
+        copy-in stream   H2D(i+1) ───────────────►
+        compute stream          HotPath.step(i) ─►
+        copy-out stream                 counts/boxes(i) ─► [host reads the crop byte count] ─► pixels(i-1)
+
+    `depth` batches are in flight over depth+1 slots (device input buffers + a HotPath with its own
+    outputs + pinned result buffers). `submit()` never blocks on the batch it enqueues; it returns the
+    finished results of the batch submitted `depth` calls earlier (None while the pipeline fills) —
+    views of that slot's pinned buffers, valid until the next `submit()` — and `flush()` drains.
+    The only host waits are on events of batches that are already behind the GPU.
+    """
+
+    SMALL = ("det_boxes", "det_scores", "det_labels", "det_counts", "crop_rects", "crop_xywh", "crop_src",
+             "crop_offsets", "crop_totals")
+
+    def __init__(self, make_hot_path, host_example, depth: int = 2, on_computed=None, on_collect=None):
+        """make_hot_path() -> HotPath (called once per slot); host_example: dict name -> list of host
+        tensors (objectness, deltas, features, class_logits, box_regression, images) giving shapes,
+        dtypes and memory formats; on_computed(hp, slot) is called with the compute stream current right
+        after a batch's kernels were enqueued (the mosaic exchange hooks in here)."""
+        self.slots = []
+        for _ in range(depth + 1):
+            hp = make_hot_path()
+            dev = hp.dev
+            d = {k: [torch.empty_like(t, device=dev) for t in v] for k, v in host_example.items()}
+            hp.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
+            out = {k: torch.empty_like(getattr(hp, k), device="cpu").pin_memory() for k in self.SMALL}
+            pix = torch.empty((hp.crop_capacity,), dtype=torch.uint8).pin_memory()
+            ev = {k: torch.cuda.Event() for k in ("h2d", "computed", "small", "pix")}
+            self.slots.append({"hp": hp, "dev": d, "out": out, "pix": pix, "ev": ev, "state": "free", "nb": 0})
+        self.dev = self.slots[0]["hp"].dev
+        self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(device=self.dev) for _ in range(3))
+        self.on_computed, self.on_collect = on_computed, on_collect
+        self.i = 0
+        self.h2d_bytes = sum(t.numel() * t.element_size() for v in host_example.values() for t in v)
+
+    def _pixels(self, slot):
+        """Second half of a batch's read-back: needs the byte count the first half brought."""
+        if slot["state"] != "small":
+            return
+        slot["ev"]["small"].synchronize()
+        tot = slot["out"]["crop_totals"]
+        if int(tot[2]):
+            raise MisoB200Error(f"crop buffer too small: {int(tot[1])} bytes needed")
+        nb = slot["nb"] = int(tot[1])
+        with torch.cuda.stream(self.s_out):
+            slot["pix"][:nb].copy_(slot["hp"].crop_pixels[:nb], non_blocking=True)
+            slot["ev"]["pix"].record(self.s_out)
+        slot["state"] = "pix"
+
+    def _collect(self, slot):
+        if slot["state"] == "free":
+            return None
+        self._pixels(slot)
+        slot["ev"]["pix"].synchronize()
+        slot["state"] = "free"
+        extra = self.on_collect(slot["hp"], slot) if self.on_collect else None
+        return {"out": slot["out"], "pixels": slot["pix"][:slot["nb"]], "extra": extra}
+
+    def submit(self, host):
+        n = len(self.slots)
+        slot, prev, nxt = self.slots[self.i % n], self.slots[(self.i - 1) % n], self.slots[(self.i + 1) % n]
+        assert slot["state"] == "free"                   # collected by the previous call (or never used)
+        with torch.cuda.stream(self.s_in):
+            for k, hs in host.items():
+                for src, dst in zip(hs, slot["dev"][k]):
+                    dst.copy_(src, non_blocking=True)
+            slot["ev"]["h2d"].record(self.s_in)
+        with torch.cuda.stream(self.s_cmp):
+            self.s_cmp.wait_event(slot["ev"]["h2d"])
+            slot["hp"].step()
+            slot["ev"]["computed"].record(self.s_cmp)
+            if self.on_computed:
+                self.on_computed(slot["hp"], slot)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot["ev"]["computed"])
+            for k, ht in slot["out"].items():
+                ht.copy_(getattr(slot["hp"], k), non_blocking=True)
+            slot["ev"]["small"].record(self.s_out)
+        slot["state"] = "small"
+        if prev is not slot:
+            self._pixels(prev)                           # batch i-1 computed while batch i's inputs were copied
+        self.i += 1
+        return self._collect(nxt)                        # batch i-depth; frees the slot the next call will use
+
+    def flush(self):
+        res = []
+        for j in range(1, len(self.slots) + 1):
+            r = self._collect(self.slots[(self.i + j) % len(self.slots)])
+            if r is not None:
+                res.append(r)
+        return res
+
+
+class OverlappedHotPath:
+    """Software-pipelined plan for a stream of batches whose inputs are already in HBM.
+
+    The RPN stage and the detection/crop stages are chains of small latency-bound kernels (a few
+    CTAs each: one per image x level or image x class segment); RoIAlign is the one kernel that
+    fills the machine. Run back to back they leave most SMs idle for half of the step, so three
+    batches are kept in flight on three streams:
+
+        stream R   rpn(k+2) ────────►
+        stream A        roi_align(k+1) ───────►
+        stream D              detections(k), crops(k) ─►
+
+    Inside one batch the order of the reference is kept (rpn -> roi_align -> detections -> crops,
+    chained by events); `slots` HotPath instances own the per-batch intermediates (proposals,
+    box features, detections, crops). `submit()` only enqueues; `drain()` makes the current stream
+    wait for everything in flight.
+    """
+
+    def __init__(self, hot_paths: Sequence[HotPath]):
+        self.hps = list(hot_paths)
+        self.dev = self.hps[0].dev
+        # the small-kernel chains get the higher stream priority: their few CTAs are placed as soon as
+        # RoIAlign CTAs retire instead of waiting for its whole grid to drain
+        self.sR = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.sA = torch.cuda.Stream(device=self.dev, priority=0)
+        self.sD = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.ev = [{k: torch.cuda.Event() for k in ("rpn", "roi", "done")} for _ in self.hps]
+        self.used = [False] * len(self.hps)
+        self.k = 0
+        self.hooks = {}          # "after_rpn" / "after_roi" / "after_det": fn(slot_index, hp, stream) for timing events, exchanges
+
+    def _c(self, s):
+        return C.c_void_p(s.cuda_stream)
+
+    def submit(self) -> int:
+        i = self.k % len(self.hps)
+        hp, ev = self.hps[i], self.ev[i]
+        if not self.used[i]:             # first use: order behind whatever prepared the inputs on the current stream
+            cur = torch.cuda.current_stream(self.dev)
+            for s in (self.sR, self.sA, self.sD):
+                s.wait_stream(cur)
+        else:
+            self.sR.wait_event(ev["done"])   # the slot's proposals / detections are free again
+        self.used[i] = True
+        with torch.cuda.stream(self.sR):
+            hp.rpn(self._c(self.sR))
+            ev["rpn"].record(self.sR)
+            if "after_rpn" in self.hooks:
+                self.hooks["after_rpn"](i, hp, self.sR)
+        with torch.cuda.stream(self.sA):
+            self.sA.wait_event(ev["rpn"])
+            if "before_roi" in self.hooks:
+                self.hooks["before_roi"](i, hp, self.sA)
+            hp.roi_align(self._c(self.sA))
+            ev["roi"].record(self.sA)
+            if "after_roi" in self.hooks:
+                self.hooks["after_roi"](i, hp, self.sA)
+        with torch.cuda.stream(self.sD):
+            self.sD.wait_event(ev["roi"])
+            if "before_det" in self.hooks:
+                self.hooks["before_det"](i, hp, self.sD)
+            hp.detections(self._c(self.sD))
+            if "after_det" in self.hooks:
+                self.hooks["after_det"](i, hp, self.sD)
+            hp.crops(self._c(self.sD))
+            ev["done"].record(self.sD)
+        self.k += 1
+        return i
+
+    def drain(self) -> None:
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.sR, self.sA, self.sD):
+            cur.wait_stream(s)

@@ -208,3 +208,36 @@ def test_roi_align_channels_last_features_bit_identical(ops, golden_dir):
         xc = cu(x).contiguous(memory_format=torch.channels_last)
         out = ops.roi_align(xc, cu(rois), P, scale, sr, aligned).cpu().numpy()
         assert np.array_equal(out, native.roi_align(x, rois, scale, P, P, sr, aligned)), name
+
+
+def test_roi_align_separable_fast_mode_channels_last(ops):
+    """exact=False on channels-last maps takes the separable merged-tap kernel (k_roi_align_nhwc_sep):
+    same mathematical sum, different association -> within 1e-5 (relative + feature scale), the
+    tolerance north_star states for RoIAlign; covers border clamps, out-of-image samples, tiny RoIs
+    (several samples on one pixel row), aligned/unaligned, 7x7 and 14x14, dead slots."""
+    for name, x, rois, scale, P, sr, aligned in cases.roi_align_cases():
+        if sr != 2 or x.shape[1] % 4:
+            continue
+        xc = cu(x).contiguous(memory_format=torch.channels_last)
+        out = ops.roi_align(xc, cu(rois), P, scale, sr, aligned, exact=False).cpu().numpy()
+        ref = native.roi_align(x, rois, scale, P, P, sr, aligned)
+        tol = 1e-5 * np.abs(ref) + 1e-5 * np.abs(x).max()
+        assert np.all(np.abs(out - ref) <= tol), name
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2, 64, 50, 60)).astype(np.float32)
+    tiny = np.concatenate([rng.integers(0, 2, (300, 1)).astype(np.float32),
+                           cases.stress_rois(rng, 300, (200, 240))], 1).astype(np.float32)
+    tiny[:100, 3:] = tiny[:100, 1:3] + rng.uniform(0.0, 6.0, (100, 2)).astype(np.float32)   # sub-bin-sized boxes
+    tiny[100:120, 1:] = np.array([-50, -50, -20, -20], np.float32)                       # fully outside
+    for P in (7, 14):
+        xc = cu(x).contiguous(memory_format=torch.channels_last)
+        out = ops.roi_align(xc, cu(tiny), P, 0.25, 2, False, exact=False).cpu().numpy()
+        ref = native.roi_align(x, tiny, 0.25, P, P, 2, False)
+        assert np.all(np.abs(out - ref) <= 1e-5 * np.abs(ref) + 1e-5 * np.abs(x).max()), P
+    feats, boxes, shapes = cases.multiscale_case()
+    xm = {str(i): cu(f).contiguous(memory_format=torch.channels_last) for i, f in enumerate(feats)}
+    for P in (7, 14):
+        fast = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], P, 2, exact=False)(xm, [cu(b) for b in boxes], shapes).cpu().numpy()
+        ref = D.multiscale_roi_align(feats, boxes, shapes, P, 2)
+        fmax = max(float(np.abs(f).max()) for f in feats)
+        assert np.all(np.abs(fast - ref) <= 1e-5 * np.abs(ref) + 1e-5 * fmax), P

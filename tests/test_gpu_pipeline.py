@@ -110,3 +110,73 @@ def test_hot_path_full_size_config2_properties():
         keep = ops.batched_nms(hp.det_boxes_net[i, :dc[i]], hp.det_scores[i, :dc[i]], hp.det_labels[i, :dc[i]], 0.5,
                                strategy="vanilla")
         assert keep.numel() == dc[i]
+
+
+def test_host_pipeline_matches_single_steps():
+    """HostPipeline (pinned host in/out, three streams, two slots) on a sequence of different
+    batches: every batch's read-back equals a plain bind + step + sync of the same inputs."""
+    from miso_b200 import pipeline, workload
+    ws = [workload.faster_rcnn_batch(num_images=2, original=320, resized=256, channels=16, post_nms_top_n=200,
+                                     detections_per_img=50, seed=s, pin=True) for s in range(5)]
+    w0 = ws[0]
+
+    def make():
+        return pipeline.HotPath(w0.shapes, w0.rpn, w0.det, threshold=w0.threshold, crop_capacity_bytes=8 << 20, device=DEV)
+
+    pipe = pipeline.HostPipeline(make, w0.host)
+    got = []
+    for w in ws:
+        r = pipe.submit(w.host)
+        if r is not None:
+            got.append({k: v.clone() for k, v in r["out"].items()} | {"pixels": r["pixels"].clone()})
+    for r in pipe.flush():
+        got.append({k: v.clone() for k, v in r["out"].items()} | {"pixels": r["pixels"].clone()})
+    assert len(got) == len(ws)
+    hp = make()
+    for w, g in zip(ws, got):
+        d = workload.to_device(w, DEV)
+        hp.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
+        hp.step(); torch.cuda.synchronize()
+        tot = hp.crop_totals.tolist()
+        assert g["crop_totals"].tolist() == tot and tot[0] > 0
+        dc = hp.det_counts.cpu()
+        assert torch.equal(g["det_counts"], dc)
+        for i in range(2):
+            for k in ("det_labels", "det_boxes", "det_scores"):
+                assert torch.equal(g[k][i, : dc[i]], getattr(hp, k)[i, : dc[i]].cpu()), k
+        for k in ("crop_rects", "crop_xywh", "crop_src"):
+            assert torch.equal(g[k][: tot[0]], getattr(hp, k)[: tot[0]].cpu()), k
+        assert torch.equal(g["crop_offsets"][: tot[0] + 1], hp.crop_offsets[: tot[0] + 1].cpu())
+        assert torch.equal(g["pixels"], hp.crop_pixels[: tot[1]].cpu())
+
+
+def test_overlapped_plan_equals_serial_steps():
+    """Three batches in flight on three streams (OverlappedHotPath), each slot bound to DIFFERENT
+    inputs, many rounds: every slot ends with exactly the results of a plain serial step."""
+    from miso_b200 import pipeline
+    built = [build(seed=s) for s in (5, 6, 7)]
+    want = []
+    for w, hp in built:
+        hp.step(); torch.cuda.synchronize()
+        want.append([t.clone() for t in (hp.proposals, hp.prop_counts, hp.box_features, hp.det_boxes, hp.det_scores,
+                                         hp.det_labels, hp.det_counts, hp.crop_totals, hp.crop_rects)]
+                    + [hp.crop_pixels[: int(hp.crop_totals[1])].clone()])
+        for t in (hp.proposals, hp.box_features, hp.det_boxes, hp.det_scores, hp.crop_pixels):
+            t.fill_(7)                      # poison: the overlapped run must rewrite everything
+    plan = pipeline.OverlappedHotPath([hp for _, hp in built])
+    for _ in range(12):
+        plan.submit()
+    plan.drain()
+    torch.cuda.synchronize()
+    for (w, hp), ref in zip(built, want):
+        got = [hp.proposals, hp.prop_counts, hp.box_features, hp.det_boxes, hp.det_scores, hp.det_labels, hp.det_counts,
+               hp.crop_totals, hp.crop_rects, hp.crop_pixels[: int(hp.crop_totals[1])]]
+        pc, dc = hp.prop_counts.cpu(), hp.det_counts.cpu()
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[6], ref[6]) and torch.equal(got[7], ref[7])
+        assert torch.equal(got[2], ref[2])                                   # RoIAlign output incl. zeroed dead slots
+        for i in range(w.shapes.num_images):
+            assert torch.equal(got[0][i, : pc[i]], ref[0][i, : pc[i]])
+            for j in (3, 4, 5):
+                assert torch.equal(got[j][i, : dc[i]], ref[j][i, : dc[i]])
+        k = int(ref[7][0])
+        assert torch.equal(got[8][:k], ref[8][:k]) and torch.equal(got[9], ref[9])

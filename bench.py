@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--fast-roi-align", action="store_true", help="FMA RoIAlign (<=1e-5) instead of the bit-exact order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--serial", action="store_true", help="one batch at a time on one stream (no cross-batch overlap)")
+    ap.add_argument("--serial", action="store_true", help="skip the additional three-batches-in-flight measurement")
     ap.add_argument("--features-layout", default="channels_last", choices=["channels_last", "nchw"],
                     help="memory format of the synthetic FPN maps: channels_last = what a torch.channels_last "
                          "cuDNN backbone produces (gathered in place); nchw = the reference's default layout")
@@ -280,25 +280,28 @@ def run_ours(args):
     origins = torch.tensor([[rank * 896.0, i * 896.0] for i in range(n)], dtype=torch.float32, device=dev)
     seam = mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev) if world > 1 else None
 
-    # Three batches in flight (pipeline.OverlappedHotPath): the RPN stage of batch k+2 and the detection/crop
-    # stages of batch k are chains of few-CTA kernels that run beside batch k+1's RoIAlign. Every batch still
-    # runs rpn -> roi_align -> detections -> crops in the reference's order (event-chained).
-    slots = 1 if args.serial else 3
+    # The timed region runs one batch at a time (rpn -> roi_align -> detections -> crops, event-chained), so that
+    # the RoIAlign launch durations and their share of the step are those of the kernel running alone. A second
+    # measurement ("pipelined") keeps three batches in flight on three streams (pipeline.OverlappedHotPath): the
+    # few-CTA kernel chains of the RPN and detection stages then run beside another batch's RoIAlign.
     hps = [hp]
-    for _ in range(slots - 1):
-        h2 = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=64 << 20,
-                              exact_roi_align=not args.fast_roi_align, device=dev)
-        h2.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
-        hps.append(h2)
-    plan = pipeline.OverlappedHotPath(hps)
+    if not args.serial:
+        for _ in range(2):
+            h2 = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=64 << 20,
+                                  exact_roi_align=not args.fast_roi_align, device=dev)
+            h2.bind(d["objectness"], d["deltas"], d["features"], d["class_logits"][0], d["box_regression"][0], d["images"])
+            hps.append(h2)
+    plan1 = pipeline.OverlappedHotPath(hps[:1])
+    plan3 = pipeline.OverlappedHotPath(hps) if len(hps) > 1 else None
 
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     ev_det = [torch.cuda.Event() for _ in hps]
     ev_pack = [None for _ in hps]
     roi_ev = []           # (start, end) CUDA events around every RoIAlign launch of the timed region, on its stream
+    recording = [False]
 
     def before_roi(i, hp_i, st):
-        if roi_ev is not None and recording[0]:
+        if recording[0]:
             e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             roi_ev.append(e)
             e[0].record(st)
@@ -312,7 +315,7 @@ def run_ours(args):
             st.wait_event(ev_pack[i])        # the previous exchange has read this slot's detection buffers
 
     def after_det(i, hp_i, st):
-        """The path's one exchange, on its own stream so that it overlaps the following batches:
+        """The path's one exchange, on its own stream so that it overlaps the following batch:
         fixed-size blocks -> one all_gather_into_tensor -> seam NMS right behind it, no host sync."""
         if world == 1:
             return
@@ -324,12 +327,12 @@ def run_ours(args):
             ev_pack[i] = torch.cuda.Event(); ev_pack[i].record(comm)
             seam.launch(mosaic.exchange(block, world), w.det.nms_thresh)
 
-    recording = [False]
-    plan.hooks.update(before_roi=before_roi, after_roi=after_roi, before_det=before_det, after_det=after_det)
-
+    for pl in (plan1, plan3):
+        if pl is not None:
+            pl.hooks.update(before_roi=before_roi, after_roi=after_roi, before_det=before_det, after_det=after_det)
     host_enqueue = [0.0]
 
-    def run_steps(k):
+    def run_steps(plan, k):
         t_h = time.perf_counter()
         for _ in range(k):
             plan.submit()
@@ -338,7 +341,22 @@ def run_ours(args):
         if world > 1:
             torch.cuda.current_stream(dev).wait_stream(comm)     # the region ends with the last seam NMS
 
-    run_steps(max(args.warmup, 3))
+    def timed(plan, k):
+        """K batches submitted and completed between two events on the current stream; max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        run_steps(plan, k)
+        e1.record()
+        barrier()
+        t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms[0])
+
+    run_steps(plan1, max(args.warmup, 3))
+    if plan3 is not None:
+        run_steps(plan3, max(args.warmup, 3))
     barrier()
     tot = hp.crop_totals.tolist()
     if tot[2]:
@@ -348,7 +366,7 @@ def run_ours(args):
     for h2 in hps[1:]:
         assert h2.crop_totals.tolist() == tot
 
-    # ---- stage breakdown from a short serial pass (one batch at a time on one stream; not the timed region) ----
+    # ---- stage breakdown from a short pass with events between the stages (not the timed region) ----
     sev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(5)]
     for es in sev:
         es[0].record(); hp.rpn(); es[1].record(); hp.roi_align(); es[2].record(); hp.detections(); es[3].record()
@@ -357,29 +375,29 @@ def run_ours(args):
     names = ("rpn", "roi_align", "det_postprocess", "filter_crop")
     serial_stage_ms = {nm: sorted(es[j].elapsed_time(es[j + 1]) for es in sev)[len(sev) // 2] for j, nm in enumerate(names)}
 
-    # ---- timed region: K steps (K batches submitted and completed), device timed; RoIAlign launches bracketed ----
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    # ---- timed region: K steps, device timed; every RoIAlign launch bracketed by events on its stream ----
     wall0 = time.time()
     recording[0] = True
-    ev0.record()
-    run_steps(args.steps)
-    ev1.record()
+    ms = timed(plan1, args.steps)
     recording[0] = False
-    barrier()
     clocks = sampler.summary(wall0, time.time()) if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms, float(dets_per_step)], dtype=torch.float64, device=dev)
+    host_ms = 1e3 * host_enqueue[0]
+    t = torch.tensor([float(dets_per_step)], dtype=torch.float64, device=dev)
     if world > 1:
-        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, total_dets = float(mx[0]), float(sm[1])
-    else:
-        total_dets = float(dets_per_step)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_dets = float(t[0])
     ms_per_step = ms / args.steps
     value = total_dets / (ms_per_step * 1e-3)
     roi_ms = sorted(e[0].elapsed_time(e[1]) for e in roi_ev)
     roi_mean_ms = sum(roi_ms) / len(roi_ms)
+
+    # ---- the same K batches, three in flight ----
+    pipelined = None
+    if plan3 is not None:
+        k3 = 3 * max(args.steps // 3, 1)
+        ms3 = timed(plan3, k3) / k3
+        pipelined = {"value": total_dets / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "steps": k3, "batches_in_flight": 3,
+                     "note": "rpn(k+2) | roi_align(k+1) | detections+crops(k) on three streams, per-batch stage order kept by events"}
 
     # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step, through the public host-facing
     # API (pipeline.HostPipeline: copy-in / compute / copy-out streams, two slots) ----
@@ -443,8 +461,8 @@ def run_ours(args):
     scl = [q.spatial_scale[i] for i in range(q.num_levels)]
     alg_bytes, k_live, touched = roi_align_algorithmic_bytes(props, cnts, w.shapes, thr, scl, w.shapes.channels, w.shapes.pooled)
     achieved = alg_bytes / (roi_mean_ms * 1e-3) / 1e9
-    nchw_route = "k_nchw_to_nhwc+k_roi_align_nhwc4" if hp.roi_ws is not None else "k_roi_align_sr2"
-    roi_kernel = "k_roi_align_nhwc4" if hp.features_layout == "channels_last" else nchw_route
+    nchw_route = "k_nchw_to_nhwc+k_roi_align_nhwc4d" if hp.roi_ws is not None else "k_roi_align_sr2"
+    roi_kernel = "k_roi_align_nhwc4d" if hp.features_layout == "channels_last" else nchw_route
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
     if os.path.exists(tpath):
@@ -460,15 +478,12 @@ def run_ours(args):
         "config": {"workload": w.name, "per_gpu_batch": args.batch, "features_layout": hp.features_layout, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
                    "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step on a second stream (overlaps the next batch)" if world > 1 else "single GPU",
-                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes,
-                   "batches_in_flight": slots,
-                   "overlap": ("3 batches in flight on 3 streams: rpn(k+2) | roi_align(k+1) | detections+crops(k); "
-                               "per-batch stage order kept by events") if slots > 1 else "none (serial)"},
+                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
         "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
                      "kernel_share_of_step": roi_mean_ms / ms_per_step},
-        "serial_stage_ms": serial_stage_ms, "host_enqueue_ms_per_step": 1e3 * host_enqueue[0],
+        "stage_ms": serial_stage_ms, "host_enqueue_ms_per_step": host_ms, "pipelined": pipelined,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps,
                 "api": "miso_b200.pipeline.HostPipeline (pinned host in/out, copy-in | compute | copy-out streams, 2 batches in flight)"},

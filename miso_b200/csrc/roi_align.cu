@@ -1,4 +1,4 @@
-// roi_align.cu — MultiScaleRoIAlign / roi_align forward for NCHW fp32 features.
+// roi_align.cu — MultiScaleRoIAlign / roi_align forward for fp32 features (NCHW or channels-last).
 //
 // Replaces tv:ops/poolers.py:147-227 (per-level where/gather/roi_align/scatter loop) and
 // torchvision::roi_align (tv:ops/roi_align.py:203-260 -> tv-csrc:ops/cuda/roi_align_kernel.cu:470)
@@ -7,16 +7,18 @@
 // computed with one fp32 rounding per operation, and in `exact` mode the bilinear sum keeps the
 // reference's operation order so results are bit-identical; otherwise FMAs are used (<=1e-5 rel).
 //
-// Staged kernel (sampling_ratio > 0, the detection models' configuration):
-//   CTA = (RoI, 32-channel chunk). The RoI's bilinear footprint (all rows/columns its samples
-//   touch) is copied once from the NCHW planes into shared memory as [channel][row][col] with a
-//   plane pitch == 1 (mod 32) words, so that "lane = channel" reads of one tap hit 32 distinct
-//   banks. Tap indices and weights are warp-uniform and computed once per RoI. Outputs are
-//   collected in shared memory and written as one contiguous, 16-byte-vectorised block of
-//   32*PH*PW floats (the [K,C,PH,PW] layout makes a channel chunk of one RoI contiguous).
-//   Footprints larger than the staging buffer are processed in groups of output rows; a
-//   footprint whose single output row does not fit falls back to direct global gathers.
-// Direct kernel (sampling_ratio <= 0 or very large bins): one thread per output element.
+// Kernels, fastest route first (dispatch at the bottom of the file):
+//   k_roi_align_nhwc4d  channels-last maps (or NCHW maps transposed once per call by k_nchw_to_nhwc
+//                       into the caller's workspace), sampling_ratio 2, <= 64 bins, C % 4 == 0:
+//                       16-byte gathers straight from global memory, taps de-duplicated per bin.
+//   k_roi_align_nhwc    channels-last, scalar gathers (14x14 mask head, odd channel counts).
+//   k_roi_align_sr2     NCHW maps without a workspace: CTA = RoI, the footprint of 32 channels is
+//                       staged NCHW -> shared memory [channel][row][col] with a plane pitch == 1
+//                       (mod 32) words so that "lane = channel" tap reads hit 32 banks.
+//   k_roi_align_staged  any other fixed sampling_ratio; k_roi_align_direct: adaptive sampling
+//                       (sampling_ratio <= 0) or very large bins, one thread per output element.
+// All of them collect a RoI's outputs in shared memory and write them as one contiguous block
+// (the [K,C,PH,PW] layout makes a channel chunk of one RoI contiguous).
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -588,239 +590,6 @@ __global__ void __launch_bounds__(kRoiThreads, 4) k_roi_align_sr2(const mb_roi_a
 }
 
 // ------------------------------------------------------------------------------------------
-// Pipelined variant of the sampling_ratio == 2 kernel: the CTA is split into 4 producer warps
-// and 8 consumer warps that hand footprints over through a 2-stage shared-memory ring guarded
-// by mbarriers (full/empty per stage). Producers only stage (global -> registers -> smem) and
-// absorb the global-load latency; consumers only read shared memory (bins) and write results,
-// so neither side ever waits at a CTA-wide barrier for the other's phase.
-// ------------------------------------------------------------------------------------------
-constexpr int kPipeConsumers = 256, kPipeProducers = 128, kPipeThreads = kPipeConsumers + kPipeProducers;
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
-    const unsigned addr = smem_u32(bar);
-    int spins = 0;
-    while (true) {
-        unsigned done;
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) break;
-        if (++spins > (1 << 26)) __trap();   // a protocol bug must fault, never hang the GPU
-    }
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kPipeThreads, 2) k_roi_align_sr2_pipe(const mb_roi_align_params p,
-                                                                      const float* __restrict__ rois,
-                                                                      float* __restrict__ out, int* __restrict__ levels_out,
-                                                                      int patch_floats) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ Tap ytab[32], xtab[32];
-    __shared__ int grp_ph0[kMaxGroups + 1], grp_y0[kMaxGroups], grp_rows[kMaxGroups], grp_direct[kMaxGroups];
-    __shared__ int s_ngroups;
-    __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2];
-
-    const int k = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
-    const int opitch = (nbins & 1) ? nbins : nbins + 1;
-    const int obuf = (kChunk * opitch + 3) & ~3;            // floats per output buffer, 16-byte multiple
-    float* out_s = smem;                                    // [2][kChunk][opitch]
-    float* patch = out_s + 2 * obuf;                        // [2][patch_floats]
-    int4* tab_off = reinterpret_cast<int4*>(patch + 2 * patch_floats);   // [nbins][4], byte offsets
-    float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);      // [nbins][4]
-
-    float r[5];
-    load_roi(rois, k, p, r);
-    RoiGeom g;
-    roi_geometry(r, p, g);
-    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
-    const int ny = PH * 2, nx = PW * 2;
-    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
-    if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
-    if (tid == 128) { mbar_init(&bar_full[0], kPipeProducers); mbar_init(&bar_full[1], kPipeProducers);
-                      mbar_init(&bar_empty[0], kPipeConsumers); mbar_init(&bar_empty[1], kPipeConsumers); }
-    __syncthreads();
-
-    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
-    const size_t plane = (size_t)g.H * g.W;
-    const float* feat = p.features[g.level] + (size_t)(bad_batch ? 0 : g.batch) * p.channels * plane;
-    const bool vec4 = ((g.W & 3) == 0) && ((plane & 3) == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0);
-    int x0 = 0, x1 = -1;
-    {
-        int i = 0;
-        while (i < nx && !xtab[i].valid) ++i;
-        int j = nx - 1;
-        while (j >= 0 && !xtab[j].valid) --j;
-        if (i <= j) { x0 = xtab[i].lo; x1 = xtab[j].hi; }
-    }
-    const bool empty = bad_batch || x1 < 0;
-    const int nchunks = (p.channels + kChunk - 1) / kChunk;
-    float* dst_roi = out + (size_t)k * p.channels * nbins;
-    if (empty) {   // dead row / nothing to sample: zeros, no pipeline
-        const long long total = (long long)p.channels * nbins;
-        for (long long i = tid; i < total; i += kPipeThreads) dst_roi[i] = 0.0f;
-        return;
-    }
-    if (vec4) { x0 &= ~3; x1 |= 3; }
-    const int cols = x1 - x0 + 1;
-
-    if (tid == 0) {
-        int ng = 0, ph0 = 0;
-        while (ph0 < PH) {
-            int gy0 = 0x7fffffff, gy1 = -1, ph1 = ph0;
-            while (ph1 < PH) {
-                int ny0 = gy0, ny1 = gy1;
-                for (int i = ph1 * 2; i < ph1 * 2 + 2; ++i)
-                    if (ytab[i].valid) { ny0 = min(ny0, ytab[i].lo); ny1 = max(ny1, ytab[i].hi); }
-                const int pix = (ny1 >= 0 ? ny1 - ny0 + 1 : 0) * cols;
-                if ((pix + ((33 - (pix & 31)) & 31)) * kChunk > patch_floats) break;
-                gy0 = ny0; gy1 = ny1; ++ph1;
-            }
-            const bool direct = (ph1 == ph0);
-            if (direct) {
-                ph1 = ph0 + 1;
-                for (int i = ph0 * 2; i < ph0 * 2 + 2; ++i)
-                    if (ytab[i].valid) { gy0 = min(gy0, ytab[i].lo); gy1 = max(gy1, ytab[i].hi); }
-            }
-            grp_ph0[ng] = ph0; grp_y0[ng] = gy1 >= 0 ? gy0 : 0; grp_rows[ng] = gy1 >= 0 ? gy1 - gy0 + 1 : 0;
-            grp_direct[ng] = direct;
-            ++ng; ph0 = ph1;
-        }
-        grp_ph0[ng] = PH;
-        s_ngroups = ng;
-    }
-    __syncthreads();
-    const int ngroups = s_ngroups;
-
-    for (int e = tid; e < nbins * 4; e += kPipeThreads) {
-        const int b = e >> 2, smp = e & 3;
-        const int ph = b / PW, pw = b - ph * PW;
-        int gi = 0;
-        while (gi + 1 < ngroups && ph >= grp_ph0[gi + 1]) ++gi;
-        const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
-        const bool ok = Y.valid && X.valid;
-        const bool direct = grp_direct[gi] != 0;
-        const int rs = direct ? g.W : cols;
-        const int oy = direct ? 0 : grp_y0[gi], ox = direct ? 0 : x0;
-        const int ylo = ok ? (Y.lo - oy) * rs : 0, yhi = ok ? (Y.hi - oy) * rs : 0;
-        const int xlo = ok ? X.lo - ox : 0, xhi = ok ? X.hi - ox : 0;
-        tab_off[e] = make_int4(4 * (ylo + xlo), 4 * (ylo + xhi), 4 * (yhi + xlo), 4 * (yhi + xhi));   // bytes
-        tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncthreads();
-
-    const int nunits = nchunks * ngroups;
-    if (warp >= kPipeConsumers / 32) {
-        // =============================== PRODUCERS ===============================
-        const int ptid = tid - kPipeConsumers;
-        for (int u = 0; u < nunits; ++u) {
-            const int chunk = u / ngroups, gi = u - chunk * ngroups;
-            const int st = u & 1;
-            mbar_wait(&bar_empty[st], ((u >> 1) & 1) ^ 1);          // slot free (passes immediately the first time)
-            const int rows = grp_rows[gi], gy0 = grp_y0[gi];
-            const int P = rows * cols;
-            const int pitch = P + ((33 - (P & 31)) & 31);
-            const int c0 = chunk * kChunk;
-            const int nch = min(kChunk, p.channels - c0);
-            const float* base = feat + (size_t)c0 * plane;
-            float* pbuf = patch + st * patch_floats;
-            if (!grp_direct[gi] && P > 0) {
-                if (vec4) {
-                    const int c4 = cols >> 2, P4 = rows * c4;
-                    const int csub = ptid & 3;
-                    for (int pos4 = ptid >> 2; pos4 < P4; pos4 += kPipeProducers / 4) {
-                        const int rr = pos4 / c4, x4 = pos4 - rr * c4;
-                        const float4* src = reinterpret_cast<const float4*>(
-                            base + (size_t)csub * plane + (size_t)(gy0 + rr) * g.W + x0 + 4 * x4);
-                        float* dp = pbuf + csub * pitch + 4 * pos4;
-                        float4 v[8];
-#pragma unroll
-                        for (int cg = 0; cg < 8; ++cg)
-                            if (cg * 4 + csub < nch) v[cg] = __ldg(src + (size_t)cg * plane);
-#pragma unroll
-                        for (int cg = 0; cg < 8; ++cg)
-                            if (cg * 4 + csub < nch) {
-                                float* d = dp + cg * 4 * pitch;
-                                d[0] = v[cg].x; d[1] = v[cg].y; d[2] = v[cg].z; d[3] = v[cg].w;
-                            }
-                    }
-                } else {
-                    for (int pos = ptid; pos < P; pos += kPipeProducers) {
-                        const int rr = pos / cols, x = pos - rr * cols;
-                        const float* src = base + (size_t)(gy0 + rr) * g.W + x0 + x;
-                        float* dp = pbuf + pos;
-                        int cc = 0;
-                        for (; cc + 8 <= nch; cc += 8) {
-                            float v[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) v[q] = __ldg(src + (size_t)q * plane);
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) dp[q * pitch] = v[q];
-                            src += 8 * plane; dp += 8 * pitch;
-                        }
-                        for (; cc < nch; ++cc) { *dp = __ldg(src); src += plane; dp += pitch; }
-                    }
-                }
-            }
-            mbar_arrive(&bar_full[st]);                              // release: the staged data is visible to waiters
-        }
-    } else {
-        // =============================== CONSUMERS ===============================
-        for (int u = 0; u < nunits; ++u) {
-            const int chunk = u / ngroups, gi = u - chunk * ngroups;
-            const int st = u & 1;
-            const int rows = grp_rows[gi];
-            const int P = rows * cols;
-            const int pitch = P + ((33 - (P & 31)) & 31);
-            const int c0 = chunk * kChunk;
-            const int nch = min(kChunk, p.channels - c0);
-            float* ob = out_s + (chunk & 1) * obuf;
-            const int b0 = grp_ph0[gi] * PW, b1 = grp_ph0[gi + 1] * PW;
-            mbar_wait(&bar_full[st], (u >> 1) & 1);
-            if (grp_direct[gi]) {
-                const float* gp = feat + (size_t)(c0 + lane) * plane;
-                if (lane < nch)
-                    for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32) {
-                        int4 o4[4];
-                        for (int q = 0; q < 4; ++q) { o4[q] = tab_off[b * 4 + q]; o4[q].x >>= 2; o4[q].y >>= 2; o4[q].z >>= 2; o4[q].w >>= 2; }
-                        ob[lane * opitch + b] = bin_value<EXACT>(gp, o4, tab_w + b * 4);
-                    }
-            } else if (P == 0) {
-                for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32) ob[lane * opitch + b] = 0.0f;
-            } else if (lane < nch) {
-                const unsigned sbase = smem_u32(patch + st * patch_floats + lane * pitch);
-                for (int b = b0 + warp; b < b1; b += kPipeConsumers / 32)
-                    ob[lane * opitch + b] = bin_value_smem<EXACT>(sbase, tab_off + b * 4, tab_w + b * 4);
-            }
-            mbar_arrive(&bar_empty[st]);                             // this thread is done reading the slot
-            if (gi == ngroups - 1) {
-                // all bins of the chunk are in ob: consumer-only barrier, then the coalesced write-out.
-                // The other output buffer is in use by the next chunk meanwhile; this one is rewritten
-                // only by chunk+2, whose bins start after the next consumer barrier.
-                asm volatile("bar.sync 1, %0;" ::"n"(kPipeConsumers) : "memory");
-                float* dst = dst_roi + (size_t)c0 * nbins;
-                const int total = nch * nbins;
-                if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
-                    const float4* s4 = reinterpret_cast<const float4*>(ob);
-                    float4* d4 = reinterpret_cast<float4*>(dst);
-                    for (int i = tid; i < total / 4; i += kPipeConsumers) d4[i] = s4[i];
-                } else {
-                    for (int ch = warp; ch < nch; ch += kPipeConsumers / 32)
-                        for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
-                }
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // Channels-last features ([N, H, W, C] in memory): no staging at all. A tap of 32 consecutive
 // channels is one 128-byte line, so "lane = channel" gathers are perfectly coalesced straight from
 // global memory; the footprint of one 32-channel chunk (~330 pixels x 128 B) lives in L1 while the
@@ -926,24 +695,82 @@ __device__ __forceinline__ void rotate4(float4& a, int rot) {
     if (rot & 2) { float t = a.x; a.x = a.z; a.z = t; t = a.y; a.y = a.w; a.w = t; }
 }
 
-// Channels-last, 16-byte gathers: lane = 4 consecutive channels, a warp covers 128 channels per tap
-// (four 128-byte lines). Table loads, address arithmetic and loop overhead are amortised over 4x
-// the outputs of the scalar variant. Needs C % 4 == 0 and 16-byte aligned maps.
-constexpr int kChunk4 = 128;
+constexpr int kChunk4 = 128;   // channels per pass of the 16-byte-gather kernel (lane = 4 consecutive channels)
+
+// ------------------------------------------------------------------------------------------
+// nhwc4 with de-duplicated taps. The 16 taps of a bin are the tensor product of 4 pixel rows
+// {lo0, hi0, lo1, hi1} and 4 pixel columns of its two samples per axis. At the pyramid level the
+// LevelMapper assigns, a RoI is 14..28 pixels across, i.e. the half-bin sample spacing is 1..2
+// pixels, so most of the time hi0 == lo1 (pattern B: 3 distinct rows); boxes smaller than the
+// canonical range have both samples in the same cell (pattern A: 2 rows); only the largest have 4
+// distinct rows (pattern C). The per-axis pattern is found when the RoI's tables are built; the
+// bin body is instantiated for the 9 (row, column) pattern pairs and loads each distinct pixel once
+// (typically 3 x 3 = 9 vector loads instead of 16). The arithmetic is untouched — the same 16
+// weight x value products in the reference order, fed from shared registers — so EXACT stays
+// bit-identical. The kernel is bound by L1 wavefronts (profiles/), which is what this removes.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT, int PY, int PX>
+__device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const uint4 ro4, const uint4 co4,
+                                            const float4* __restrict__ tw) {
+    constexpr int NR = PY == 0 ? 2 : (PY == 1 ? 3 : 4), NC = PX == 0 ? 2 : (PX == 1 ? 3 : 4);
+    const unsigned ro[4] = {ro4.x, ro4.y, ro4.z, ro4.w}, co[4] = {co4.x, co4.y, co4.z, co4.w};
+    float4 G[NR][NC];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) G[r][c] = __ldg(reinterpret_cast<const float4*>(gp + (ro[r] + co[c])));
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int iy = smp >> 1, ix = smp & 1;
+        const int yl = iy == 0 ? 0 : (PY == 0 ? 0 : (PY == 1 ? 1 : 2)), yh = iy == 0 ? 1 : (PY == 0 ? 1 : (PY == 1 ? 2 : 3));
+        const int xl = ix == 0 ? 0 : (PX == 0 ? 0 : (PX == 1 ? 1 : 2)), xh = ix == 0 ? 1 : (PX == 0 ? 1 : (PX == 1 ? 2 : 3));
+        const float4 wv = tw[smp];
+        const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
+        if (EXACT) {
+#define MB_TAPSUM(acc, f)                                                                           \
+    {                                                                                               \
+        float t = __fmul_rn(wv.x, v1.f);                                                            \
+        t = __fadd_rn(t, __fmul_rn(wv.y, v2.f));                                                    \
+        t = __fadd_rn(t, __fmul_rn(wv.z, v3.f));                                                    \
+        t = __fadd_rn(t, __fmul_rn(wv.w, v4.f));                                                    \
+        acc = __fadd_rn(acc, t);                                                                    \
+    }
+            MB_TAPSUM(a0, x) MB_TAPSUM(a1, y) MB_TAPSUM(a2, z) MB_TAPSUM(a3, w)
+#undef MB_TAPSUM
+        } else {
+            a0 = fmaf(wv.x, v1.x, fmaf(wv.y, v2.x, fmaf(wv.z, v3.x, fmaf(wv.w, v4.x, a0))));
+            a1 = fmaf(wv.x, v1.y, fmaf(wv.y, v2.y, fmaf(wv.z, v3.y, fmaf(wv.w, v4.y, a1))));
+            a2 = fmaf(wv.x, v1.z, fmaf(wv.y, v2.z, fmaf(wv.z, v3.z, fmaf(wv.w, v4.z, a2))));
+            a3 = fmaf(wv.x, v1.w, fmaf(wv.y, v2.w, fmaf(wv.z, v3.w, fmaf(wv.w, v4.w, a3))));
+        }
+    }
+    return make_float4(__fmul_rn(a0, 0.25f), __fmul_rn(a1, 0.25f), __fmul_rn(a2, 0.25f), __fmul_rn(a3, 0.25f));
+}
+
+// distinct pixel indices of one bin along one axis, in the slot order the patterns expect
+__device__ __forceinline__ int axis_pattern(const Tap& A, const Tap& B, int idx[4]) {
+    idx[0] = A.lo; idx[1] = A.hi; idx[2] = B.lo; idx[3] = B.hi;
+    if (B.lo == A.lo && B.hi == A.hi) return 0;                 // A: same cell
+    if (B.lo == A.hi) { idx[2] = B.hi; return 1; }              // B: the samples share one pixel
+    return 2;                                                   // C: four pixels
+}
 
 template <bool EXACT>
-__global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi_align_params p,
-                                                                  const float* __restrict__ rois,
-                                                                  float* __restrict__ out, int* __restrict__ levels_out) {
+__global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_roi_align_params p,
+                                                                   const float* __restrict__ rois,
+                                                                   float* __restrict__ out, int* __restrict__ levels_out) {
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[32], xtab[32];
+    __shared__ uint4 s_ro[16], s_co[16];             // byte offsets of the distinct rows / columns of each bin row / column
+    __shared__ int s_py[16], s_px[16];
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
-    const int opitch = nbins | 1;                         // odd pitch: the rotated stores below are conflict-free
-    float* ob = smem;                                                  // [128][opitch]; == output layout when nbins is odd
-    int4* tab_off = reinterpret_cast<int4*>(ob + ((kChunk4 * opitch + 3) & ~3));
-    float4* tab_w = reinterpret_cast<float4*>(tab_off + nbins * 4);
+    const int opitch = nbins | 1;
+    float* ob = smem;                                                  // [128][opitch]
+    float4* tab_w = reinterpret_cast<float4*>(ob + ((kChunk4 * opitch + 3) & ~3));   // [nbins][4 samples]
+    int* s_bin = reinterpret_cast<int*>(tab_w + nbins * 4);            // [nbins] ph | pw << 8 | pattern << 16
 
     float r[5];
     load_roi(rois, k, p, r);
@@ -954,24 +781,36 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
     if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
     if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
     __syncthreads();
-    const bool bad_batch = g.batch < 0 || g.batch >= p.num_images;
     const int C = p.channels;
     float* dst_roi = out + (size_t)k * C * nbins;
-    if (bad_batch) {
+    if (g.batch < 0 || g.batch >= p.num_images) {
         for (long long i = tid; i < (long long)C * nbins; i += kRoiThreads) dst_roi[i] = 0.0f;
         return;
+    }
+    if (tid < PH) {
+        int idx[4];
+        s_py[tid] = axis_pattern(ytab[2 * tid], ytab[2 * tid + 1], idx);
+        const unsigned rb = (unsigned)g.W * (unsigned)C * 4u;
+        s_ro[tid] = make_uint4(idx[0] * rb, idx[1] * rb, idx[2] * rb, idx[3] * rb);
+    } else if (tid >= 32 && tid < 32 + PW) {
+        const int t = tid - 32;
+        int idx[4];
+        s_px[t] = axis_pattern(xtab[2 * t], xtab[2 * t + 1], idx);
+        const unsigned cb = (unsigned)C * 4u;
+        s_co[t] = make_uint4(idx[0] * cb, idx[1] * cb, idx[2] * cb, idx[3] * cb);
     }
     for (int e = tid; e < nbins * 4; e += kRoiThreads) {
         const int b = e >> 2, smp = e & 3;
         const int ph = b / PW, pw = b - ph * PW;
         const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
-        const bool ok = Y.valid && X.valid;
-        const int cb = C * 4;
-        const int ylo = ok ? Y.lo * g.W : 0, yhi = ok ? Y.hi * g.W : 0;
-        const int xlo = ok ? X.lo : 0, xhi = ok ? X.hi : 0;
-        tab_off[e] = make_int4((ylo + xlo) * cb, (ylo + xhi) * cb, (yhi + xlo) * cb, (yhi + xhi) * cb);
-        tab_w[e] = ok ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        tab_w[e] = (Y.valid && X.valid)
+                       ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int b = tid; b < nbins; b += kRoiThreads) {
+        const int ph = b / PW, pw = b - ph * PW;
+        s_bin[b] = ph | (pw << 8) | ((s_py[ph] * 3 + s_px[pw]) << 16);
     }
     __syncthreads();
     const char* img = reinterpret_cast<const char*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C * 4;
@@ -986,44 +825,27 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
         if (4 * lane < nch) {
             const char* gp = img + (size_t)(c0 + 4 * lane) * 4;
             for (int b = warp; b < nbins; b += kRoiWarps) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-                for (int smp = 0; smp < 4; ++smp) {
-                    const int4 o = tab_off[b * 4 + smp];
-                    const float4 wv = tab_w[b * 4 + smp];
-                    const float4 v1 = __ldg(reinterpret_cast<const float4*>(gp + o.x));
-                    const float4 v2 = __ldg(reinterpret_cast<const float4*>(gp + o.y));
-                    const float4 v3 = __ldg(reinterpret_cast<const float4*>(gp + o.z));
-                    const float4 v4 = __ldg(reinterpret_cast<const float4*>(gp + o.w));
-                    if (EXACT) {
-#define MB_TAPSUM(acc, f)                                                                           \
-    {                                                                                               \
-        float t = __fmul_rn(wv.x, v1.f);                                                            \
-        t = __fadd_rn(t, __fmul_rn(wv.y, v2.f));                                                    \
-        t = __fadd_rn(t, __fmul_rn(wv.z, v3.f));                                                    \
-        t = __fadd_rn(t, __fmul_rn(wv.w, v4.f));                                                    \
-        acc = __fadd_rn(acc, t);                                                                    \
-    }
-                        MB_TAPSUM(a0, x) MB_TAPSUM(a1, y) MB_TAPSUM(a2, z) MB_TAPSUM(a3, w)
-#undef MB_TAPSUM
-                    } else {
-                        a0 = fmaf(wv.x, v1.x, fmaf(wv.y, v2.x, fmaf(wv.z, v3.x, fmaf(wv.w, v4.x, a0))));
-                        a1 = fmaf(wv.x, v1.y, fmaf(wv.y, v2.y, fmaf(wv.z, v3.y, fmaf(wv.w, v4.y, a1))));
-                        a2 = fmaf(wv.x, v1.z, fmaf(wv.y, v2.z, fmaf(wv.z, v3.z, fmaf(wv.w, v4.z, a2))));
-                        a3 = fmaf(wv.x, v1.w, fmaf(wv.y, v2.w, fmaf(wv.z, v3.w, fmaf(wv.w, v4.w, a3))));
-                    }
+                const int info = s_bin[b];
+                const uint4 ro4 = s_ro[info & 0xff], co4 = s_co[(info >> 8) & 0xff];
+                const float4* tw = tab_w + b * 4;
+                float4 av;
+                switch (info >> 16) {      // warp-uniform
+                    case 0: av = bin_dedup<EXACT, 0, 0>(gp, ro4, co4, tw); break;
+                    case 1: av = bin_dedup<EXACT, 0, 1>(gp, ro4, co4, tw); break;
+                    case 2: av = bin_dedup<EXACT, 0, 2>(gp, ro4, co4, tw); break;
+                    case 3: av = bin_dedup<EXACT, 1, 0>(gp, ro4, co4, tw); break;
+                    case 4: av = bin_dedup<EXACT, 1, 1>(gp, ro4, co4, tw); break;
+                    case 5: av = bin_dedup<EXACT, 1, 2>(gp, ro4, co4, tw); break;
+                    case 6: av = bin_dedup<EXACT, 2, 0>(gp, ro4, co4, tw); break;
+                    case 7: av = bin_dedup<EXACT, 2, 1>(gp, ro4, co4, tw); break;
+                    default: av = bin_dedup<EXACT, 2, 2>(gp, ro4, co4, tw); break;
                 }
-                // Channel 4*lane+j goes to row 4*lane+j. Storing j in the order (lane/8 + t) % 4 spreads the
-                // four lanes that share (4*lane*nbins mod 32) over different j, i.e. over different banks.
-                a0 = __fmul_rn(a0, 0.25f); a1 = __fmul_rn(a1, 0.25f); a2 = __fmul_rn(a2, 0.25f); a3 = __fmul_rn(a3, 0.25f);
-                float4 av = make_float4(a0, a1, a2, a3);
                 rotate4(av, rot4);
                 float* o = ob + (4 * lane) * opitch + b;
                 o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
             }
         }
         __syncthreads();
-        // write out: the chunk is one contiguous block of nch*nbins floats in the output
         float* dst = dst_roi + (size_t)c0 * nbins;
         const int total = nch * nbins;
         if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
@@ -1035,165 +857,6 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4(const mb_roi
                 for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
         }
         __syncthreads();   // ob is reused by the next chunk
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// Channels-last, separable merged-tap gather (the `exact = 0` mode; results within 1e-5 of the
-// reference, not bit-identical). The sample grid of a RoI is a tensor product, so a bin is
-//     out[ph][pw] = 1/count * sum_y Wy[ph][y] * ( sum_x Wx[pw][x] * F[y][x] )
-// where Wy[ph] has at most four non-zero rows (two samples x two taps) and usually three, because
-// at the pyramid level the LevelMapper picks a RoI is 14..28 pixels across, the half-bin sample
-// spacing is 1..2 pixels and the two samples of a bin share a pixel row (column). Taps that fall on
-// the same row / column are merged when the per-RoI tables are built, zero-weight slots are skipped,
-// and a row that closes bin ph and opens bin ph+1 is summed once. A work item is (pw, 4 channels):
-// it walks the rows top to bottom, loads every (row, column) it needs once as one 16-byte vector
-// (consecutive lanes = consecutive channels: 512-byte coalesced), and produces the PH outputs of its
-// column. Per 4 channels that is ~7 x 17 x 3 = 360 vector loads per RoI instead of 784 — this kernel
-// is bound by L1 wavefronts, so that is where the time goes. Outputs are staged in shared memory
-// ([channel][odd pitch], rotated stores) and leave as one contiguous coalesced block.
-// ------------------------------------------------------------------------------------------
-constexpr int kSepThreads = 448;   // 7 pooled columns x 64 channel vectors (256 channels)
-
-// Merge the four taps of one pooled bin along one axis (two samples x {lo, hi}) into distinct pixel
-// indices with summed weights, compacted to the front; returns how many are left (0..4).
-__device__ __forceinline__ int merge_axis_slots(const Tap& A, const Tap& B, int r[4], float w[4]) {
-    int rr[4] = {A.lo, A.hi, B.lo, B.hi};
-    float ww[4] = {A.h, A.l, B.h, B.l};                // make_tap zeroes the weights of an out-of-range sample
-    if (rr[1] == rr[0]) { ww[0] += ww[1]; ww[1] = 0.f; }
-    if (rr[3] == rr[2]) { ww[2] += ww[3]; ww[3] = 0.f; }
-    if (rr[2] == rr[0]) { ww[0] += ww[2]; ww[2] = 0.f; } else if (rr[2] == rr[1]) { ww[1] += ww[2]; ww[2] = 0.f; }
-    if (rr[3] == rr[0]) { ww[0] += ww[3]; ww[3] = 0.f; } else if (rr[3] == rr[1]) { ww[1] += ww[3]; ww[3] = 0.f; }
-    int n = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { r[j] = 0; w[j] = 0.f; }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (ww[j] != 0.f) {
-#pragma unroll
-            for (int t = 0; t < 4; ++t) if (t == n) { r[t] = rr[j]; w[t] = ww[j]; }
-            ++n;
-        }
-    return n;
-}
-
-// R = sum over the NX merged columns of one pixel row (all loads issued before the first use)
-template <int NX>
-__device__ __forceinline__ float4 sep_row_sum(const float4* __restrict__ rp, const unsigned (&xo)[4], const float (&xw)[4]) {
-    float4 v[NX > 0 ? NX : 1];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) v[i] = __ldg(rp + xo[i]);
-    float4 R = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-        R.x = fmaf(xw[i], v[i].x, R.x); R.y = fmaf(xw[i], v[i].y, R.y);
-        R.z = fmaf(xw[i], v[i].z, R.z); R.w = fmaf(xw[i], v[i].w, R.w);
-    }
-    return R;
-}
-
-__global__ void __maxnreg__(48) k_roi_align_nhwc_sep(const mb_roi_align_params p,
-                                                                     const float* __restrict__ rois,
-                                                                     float* __restrict__ out, int* __restrict__ levels_out,
-                                                                     int chunk_c) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ unsigned s_yoff[64], s_xoff[64];   // [bin index along the axis][4 slots], units of 16 bytes
-    __shared__ float s_yw[64], s_xw[64];
-    __shared__ int s_ny[16], s_nx[16];
-    const int k = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
-    const int opitch = nbins | 1;
-    float* ob = smem;                                                  // [chunk_c][opitch]
-
-    float r[5];
-    load_roi(rois, k, p, r);
-    RoiGeom g;
-    roi_geometry(r, p, g);
-    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
-    const int C = p.channels, C4 = C >> 2;
-    float* dst_roi = out + (size_t)k * C * nbins;
-    if (g.batch < 0 || g.batch >= p.num_images) {
-        for (long long i = tid; i < (long long)C * nbins; i += blockDim.x) dst_roi[i] = 0.0f;
-        return;
-    }
-    if (tid < PH) {
-        const Tap A = make_tap(g.start_h, g.bin_h, tid, 0, 2, g.H), B = make_tap(g.start_h, g.bin_h, tid, 1, 2, g.H);
-        int rr[4]; float ww[4];
-        s_ny[tid] = merge_axis_slots(A, B, rr, ww);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            s_yoff[tid * 4 + j] = (unsigned)rr[j] * (unsigned)g.W * (unsigned)C4;
-            s_yw[tid * 4 + j] = ww[j] * 0.25f;                         // 1/count folded in (count = 4, exact scaling)
-        }
-    } else if (tid >= 32 && tid < 32 + PW) {
-        const int t = tid - 32;
-        const Tap A = make_tap(g.start_w, g.bin_w, t, 0, 2, g.W), B = make_tap(g.start_w, g.bin_w, t, 1, 2, g.W);
-        int rr[4]; float ww[4];
-        s_nx[t] = merge_axis_slots(A, B, rr, ww);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { s_xoff[t * 4 + j] = (unsigned)rr[j] * (unsigned)C4; s_xw[t * 4 + j] = ww[j]; }
-    }
-    __syncthreads();
-    const float4* img = reinterpret_cast<const float4*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C4;
-    const int chunk4 = chunk_c >> 2;
-    const int rot = lane >> 3;
-    int so[4];                                                         // smem row offsets in rotated order
-#pragma unroll
-    for (int t = 0; t < 4; ++t) so[t] = ((rot + t) & 3) * opitch;
-    for (int c0 = 0; c0 < C; c0 += chunk_c) {
-        const int n4 = min(chunk4, (C - c0) >> 2);
-        const int items = PW * n4;
-        const float inv_n4 = 1.0f / (float)n4;
-        for (int it = tid; it < items; it += blockDim.x) {
-            int pw = (int)((float)it * inv_n4);
-            if ((pw + 1) * n4 <= it) ++pw;
-            if (pw * n4 > it) --pw;
-            const int c4 = it - pw * n4;
-            const float4* gp = img + (c0 >> 2) + c4;
-            unsigned xo[4]; float xw[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { xo[i] = s_xoff[pw * 4 + i]; xw[i] = s_xw[pw * 4 + i]; }
-            const int nx = s_nx[pw];
-            unsigned prev = 0xffffffffu;
-            float4 R = make_float4(0.f, 0.f, 0.f, 0.f);
-            float* o = ob + (4 * c4) * opitch + pw;
-            for (int ph = 0; ph < PH; ++ph) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                const int ny = s_ny[ph];
-                for (int j = 0; j < ny; ++j) {
-                    const unsigned yo = s_yoff[ph * 4 + j];
-                    const float wy = s_yw[ph * 4 + j];
-                    if (yo != prev) {                                  // a row shared with the previous bin is summed once
-                        prev = yo;
-                        const float4* rp = gp + yo;
-                        if (nx == 3) R = sep_row_sum<3>(rp, xo, xw);
-                        else if (nx == 2) R = sep_row_sum<2>(rp, xo, xw);
-                        else if (nx == 4) R = sep_row_sum<4>(rp, xo, xw);
-                        else if (nx == 1) R = sep_row_sum<1>(rp, xo, xw);
-                        else R = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    acc.x = fmaf(wy, R.x, acc.x); acc.y = fmaf(wy, R.y, acc.y);
-                    acc.z = fmaf(wy, R.z, acc.z); acc.w = fmaf(wy, R.w, acc.w);
-                }
-                rotate4(acc, rot);
-                float* ob_bin = o + ph * PW;
-                ob_bin[so[0]] = acc.x; ob_bin[so[1]] = acc.y; ob_bin[so[2]] = acc.z; ob_bin[so[3]] = acc.w;
-            }
-        }
-        __syncthreads();
-        float* dst = dst_roi + (size_t)c0 * nbins;
-        const int total = 4 * n4 * nbins;
-        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(ob);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            for (int i = tid; i < total / 4; i += blockDim.x) d4[i] = s4[i];
-        } else {
-            const int nw = blockDim.x >> 5, warp = tid >> 5;
-            for (int ch = warp; ch < 4 * n4; ch += nw)
-                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
-        }
-        __syncthreads();
     }
 }
 
@@ -1317,30 +980,17 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const bool vec = (nv == nullptr || strcmp(nv, "scalar") != 0) && (p.channels % 4 == 0);
         bool aligned16 = true;
         for (int l = 0; l < p.num_levels; ++l) aligned16 = aligned16 && ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) == 0);
-        const char* sp = getenv("MB_ROI_SEP");
-        if (!p.exact && vec && aligned16 && sp != nullptr && sp[0] == '1') {   // experimental, measured slower than nhwc4
-            // separable merged-tap kernel (fast mode): channel chunk sized so that the staged outputs stay <= ~50 KB
-            int chunk_c = ((52 * 1024) / ((nbins | 1) * (int)sizeof(float))) & ~3;
-            if (chunk_c > p.channels) chunk_c = p.channels;
-            if (chunk_c >= 128) chunk_c &= ~127;                      // whole warps share one pooled column
-            if (chunk_c >= 4) {
-                const int items = p.pooled_w * (chunk_c / 4);
-                const int threads = min(kSepThreads, (items + 31) & ~31);
-                const int smem = chunk_c * (nbins | 1) * (int)sizeof(float);
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                k_roi_align_nhwc_sep<<<(int)num_rois, threads, smem, stream>>>(p, rois, out, levels_out, chunk_c);
-                MB_LAUNCH_CHECK();
-                return MB_OK;
-            }
-        }
-        if (vec && aligned16 && nbins <= 64) {   // larger bins: the scalar variant keeps more CTAs resident
-            const int smem4 = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 32;
+        bool small_maps = true;   // 32-bit byte offsets inside one image
+        for (int l = 0; l < p.num_levels; ++l)
+            small_maps = small_maps && ((unsigned long long)p.height[l] * p.width[l] * p.channels * 4ull < (1ull << 32));
+        if (vec && aligned16 && nbins <= 64 && small_maps) {   // larger bins: the scalar variant keeps more CTAs resident
+            const int smemd = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 16 + nbins * 4;
             if (p.exact) {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-                k_roi_align_nhwc4<true><<<(int)num_rois, kRoiThreads, smem4, stream>>>(p, rois, out, levels_out);
+                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
+                k_roi_align_nhwc4d<true><<<(int)num_rois, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out);
             } else {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem4));
-                k_roi_align_nhwc4<false><<<(int)num_rois, kRoiThreads, smem4, stream>>>(p, rois, out, levels_out);
+                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
+                k_roi_align_nhwc4d<false><<<(int)num_rois, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out);
             }
             MB_LAUNCH_CHECK();
             return MB_OK;
@@ -1359,27 +1009,6 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     }
     if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
-        const char* sel = getenv("MB_ROI_KERNEL");
-        const bool legacy = sel == nullptr || strcmp(sel, "pipe") != 0;   // the single-role kernel measured faster (profiles/)
-        if (!legacy) {
-            // 2 CTAs/SM: 2 output buffers + 2 footprint slots + bin tables within ~113 KB
-            const int obuf = (kChunk * opitch + 3) & ~3;
-            int pitch_cap = 353;
-            const char* pc = getenv("MB_ROI_PITCH");
-            if (pc != nullptr) pitch_cap = atoi(pc);
-            int smem = (2 * obuf + 2 * kChunk * pitch_cap) * (int)sizeof(float) + nbins * 4 * 32;
-            while (smem > 110 * 1024 && pitch_cap > 65) { pitch_cap -= 32; smem -= 2 * kChunk * 32 * (int)sizeof(float); }
-            const int patch_floats = kChunk * pitch_cap;
-            if (p.exact) {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                k_roi_align_sr2_pipe<true><<<(int)num_rois, kPipeThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
-            } else {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                k_roi_align_sr2_pipe<false><<<(int)num_rois, kPipeThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats);
-            }
-            MB_LAUNCH_CHECK();
-            return MB_OK;
-        }
         const char* vs = getenv("MB_ROI_VARIANT");
         const int variant = vs != nullptr ? atoi(vs) : 2;   // bit0: no float4 staging, bit1: 16 scalar loads in flight
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7

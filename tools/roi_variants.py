@@ -32,8 +32,7 @@ feats = [torch.randn(n, c, 800 // s, 800 // s, device=DEV) for s in (4, 8, 16, 3
 res = {}
 VARIANTS = [("legacy_vec4", {"MB_ROI_KERNEL": "legacy", "MB_ROI_VARIANT": "0"}),
             ("legacy_scalar8", {"MB_ROI_KERNEL": "legacy", "MB_ROI_VARIANT": "1"}),
-            ("legacy_scalar16", {"MB_ROI_KERNEL": "legacy", "MB_ROI_VARIANT": "3"}),
-            ("pipe353", {"MB_ROI_KERNEL": "pipe", "MB_ROI_PITCH": "353"})]
+            ("legacy_scalar16", {"MB_ROI_KERNEL": "legacy", "MB_ROI_VARIANT": "3"})]
 for P, per in ((7, 1000), (14, 100)):
     boxes = [torch.from_numpy(cases.stress_rois(rng, per, (800, 800))).to(DEV) for _ in range(n)]
     rois = ops._f32c(ops.convert_boxes_to_roi_format(boxes))

@@ -295,6 +295,8 @@ def run_ours(args):
     plan3 = pipeline.OverlappedHotPath(hps) if len(hps) > 1 else None
 
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
+    x_block = torch.empty((n * dpi, 6), dtype=torch.float32, device=dev)             # this rank's block / all ranks' blocks
+    x_gathered = torch.empty((world * n * dpi, 6), dtype=torch.float32, device=dev)  # (reused: the comm stream is in order)
     ev_det = [torch.cuda.Event() for _ in hps]
     ev_pack = [None for _ in hps]
     roi_ev = []           # (start, end) CUDA events around every RoIAlign launch of the timed region, on its stream
@@ -322,10 +324,12 @@ def run_ours(args):
         ev_det[i].record(st)
         with torch.cuda.stream(comm):
             comm.wait_event(ev_det[i])
-            block = mosaic.pack_block(hp_i.det_boxes, hp_i.det_scores, hp_i.det_labels, hp_i.det_counts, origins,
-                                      w.threshold, n * dpi)
-            ev_pack[i] = torch.cuda.Event(); ev_pack[i].record(comm)
-            seam.launch(mosaic.exchange(block, world), w.det.nms_thresh)
+            mosaic.pack_block(hp_i.det_boxes, hp_i.det_scores, hp_i.det_labels, hp_i.det_counts, origins,
+                              w.threshold, n * dpi, out=x_block)
+            if ev_pack[i] is None:
+                ev_pack[i] = torch.cuda.Event()
+            ev_pack[i].record(comm)
+            seam.launch(mosaic.exchange(x_block, world, out=x_gathered), w.det.nms_thresh)
 
     for pl in (plan1, plan3):
         if pl is not None:

@@ -218,6 +218,23 @@ int mb_crop_gather(const mb_crop_params* params_host, const int32_t* rects, cons
                    const int64_t* offsets, int64_t* totals, uint8_t* crops_out,
                    int64_t crops_capacity_bytes, mb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Tiled-mosaic exchange, element-wise ends (the reference never tiles, so
+ * there is no reference line to cite; the score filter is miso's
+ * ref:miso/object_detection/inference.py:53 `scores > threshold`).
+ * mb_mosaic_pack: detections of this rank's tiles ([tiles, dpi, 4] boxes in tile coordinates,
+ *   [tiles, dpi] scores and int64 labels, det_counts[tiles] live rows, origins_yx [tiles, 2] fp32
+ *   tile origins) -> block_out [rows, 6] = (x1, y1, x2, y2, score, label) in mosaic coordinates,
+ *   label -1 for dead / filtered / padding rows (rows >= tiles*dpi).
+ * mb_mosaic_unpack: gathered blocks [rows, 6] -> boxes [rows, 4], scores [rows], labels [rows]
+ *   int64 — the inputs of mb_nms mode 1, which ignores negative labels.
+ * ------------------------------------------------------------------------------------ */
+int mb_mosaic_pack(const float* det_boxes, const float* det_scores, const int64_t* det_labels,
+                   const int32_t* det_counts, const float* origins_yx, int32_t tiles, int32_t dpi,
+                   float threshold, int64_t rows, float* block_out, mb_stream_t stream);
+int mb_mosaic_unpack(const float* block, int64_t rows, float* boxes_out, float* scores_out,
+                     int64_t* labels_out, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

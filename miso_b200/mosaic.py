@@ -47,11 +47,27 @@ def tiles_per_rank_max(num_tiles: int, world: int) -> int:
 
 
 def pack_block(det_boxes: Tensor, det_scores: Tensor, det_labels: Tensor, det_counts: Tensor, origins: Tensor,
-               threshold: float, rows: int) -> Tensor:
+               threshold: float, rows: int, out: Optional[Tensor] = None) -> Tensor:
     """[T, dpi, *] detections of this rank's tiles -> one fixed-size block [rows, 6] =
     (x1, y1, x2, y2, score, label) in mosaic coordinates. Rows that hold no detection, or one
-    that fails `score > threshold`, get label -1. origins: [T, 2] = (y, x) as fp32 (exact)."""
+    that fails `score > threshold`, get label -1. origins: [T, 2] = (y, x) as fp32 (exact).
+    CUDA tensors: one mb_mosaic_pack launch (into `out` if given); CPU tensors (the gloo tests of
+    the host logic): the same arithmetic with tensor operations."""
     t, dpi = det_scores.shape
+    if det_boxes.is_cuda:
+        import ctypes as C
+        from . import _lib
+        from .ops import _ptr, _stream
+        if out is None:
+            out = torch.empty((rows, 6), dtype=torch.float32, device=det_boxes.device)
+        for x in (det_boxes, det_scores, det_labels, det_counts, origins, out):
+            torch._assert(x.is_contiguous(), "pack_block: contiguous tensors expected")
+        torch._assert(det_labels.dtype == torch.int64 and det_counts.dtype == torch.int32 and out.shape == (rows, 6),
+                      "pack_block: int64 labels, int32 counts, [rows, 6] output expected")
+        _lib.check(_lib.load().mb_mosaic_pack(_ptr(det_boxes), _ptr(det_scores), _ptr(det_labels), _ptr(det_counts),
+                                              _ptr(origins), int(t), int(dpi), float(threshold), int(rows), _ptr(out),
+                                              _stream(det_boxes)), "mb_mosaic_pack")
+        return out
     idx = torch.arange(dpi, device=det_scores.device)[None, :]
     live = (idx < det_counts[:, None]) & (det_scores > threshold)
     off = torch.stack([origins[:, 1], origins[:, 0], origins[:, 1], origins[:, 0]], dim=1)[:, None, :]
@@ -65,31 +81,39 @@ def pack_block(det_boxes: Tensor, det_scores: Tensor, det_labels: Tensor, det_co
     return block.contiguous()
 
 
-def exchange(block: Tensor, world: int, group=None) -> Tensor:
+def exchange(block: Tensor, world: int, group=None, out: Optional[Tensor] = None) -> Tensor:
     """The path's one collective: all-gather of the per-rank blocks, rank order preserved."""
     if world == 1:
         return block
     import torch.distributed as dist
-    out = torch.empty((world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
+    if out is None:
+        out = torch.empty((world * block.shape[0], block.shape[1]), dtype=block.dtype, device=block.device)
     dist.all_gather_into_tensor(out, block, group=group)
     return out
 
 
 class SeamNms:
-    """Sync-free seam NMS for CUDA tensors: one prepared mb_nms launch sequence over ALL gathered
-    rows (padding rows carry label -1 and are ignored on the device), enqueued on the same stream
-    right behind the all-gather. `finish()` reads the count (the step's only host sync)."""
+    """Sync-free seam NMS for CUDA tensors: one mb_mosaic_unpack launch plus one prepared mb_nms
+    launch sequence over ALL gathered rows (padding rows carry label -1 and are ignored on the
+    device), enqueued on the same stream right behind the all-gather; every buffer is allocated
+    once. `finish()` reads the count (the step's only host sync)."""
 
     def __init__(self, rows: int, num_classes: int, device):
         from .ops import PreparedBatchedNms
         self.nms = PreparedBatchedNms(rows, num_classes, device)
+        self.rows = int(rows)
+        self.boxes = torch.empty((rows, 4), dtype=torch.float32, device=device)
+        self.scores = torch.empty((rows,), dtype=torch.float32, device=device)
+        self.labels = torch.empty((rows,), dtype=torch.int64, device=device)
         self.gathered = None
 
     def launch(self, gathered: Tensor, iou_threshold: float):
+        from . import _lib
+        from .ops import _ptr, _stream
+        torch._assert(gathered.is_contiguous() and gathered.shape == (self.rows, 6), "SeamNms: [rows, 6] contiguous block expected")
         self.gathered = gathered
-        self.boxes = gathered[:, :4].contiguous()
-        self.scores = gathered[:, 4].contiguous()
-        self.labels = gathered[:, 5].to(torch.int64)
+        _lib.check(_lib.load().mb_mosaic_unpack(_ptr(gathered), self.rows, _ptr(self.boxes), _ptr(self.scores),
+                                                _ptr(self.labels), _stream(gathered)), "mb_mosaic_unpack")
         return self.nms(self.boxes, self.scores, self.labels, iou_threshold)
 
     def finish(self):

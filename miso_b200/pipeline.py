@@ -354,7 +354,8 @@ class OverlappedHotPath:
         self.ev = [{k: torch.cuda.Event() for k in ("rpn", "roi", "done")} for _ in self.hps]
         self.used = [False] * len(self.hps)
         self.k = 0
-        self.hooks = {}          # "after_rpn" / "after_roi" / "after_det": fn(slot_index, hp, stream) for timing events, exchanges
+        self.hooks = {}          # "before_roi" / "after_roi" / "before_det" / "after_det": fn(slot_index, hp, stream) —
+                                 # timing events, the mosaic exchange; hooks that enqueue work must use `stream` explicitly
 
     def _c(self, s):
         return C.c_void_p(s.cuda_stream)
@@ -369,28 +370,25 @@ class OverlappedHotPath:
         else:
             self.sR.wait_event(ev["done"])   # the slot's proposals / detections are free again
         self.used[i] = True
-        with torch.cuda.stream(self.sR):
-            hp.rpn(self._c(self.sR))
-            ev["rpn"].record(self.sR)
-            if "after_rpn" in self.hooks:
-                self.hooks["after_rpn"](i, hp, self.sR)
-        with torch.cuda.stream(self.sA):
-            self.sA.wait_event(ev["rpn"])
-            if "before_roi" in self.hooks:
-                self.hooks["before_roi"](i, hp, self.sA)
-            hp.roi_align(self._c(self.sA))
-            ev["roi"].record(self.sA)
-            if "after_roi" in self.hooks:
-                self.hooks["after_roi"](i, hp, self.sA)
-        with torch.cuda.stream(self.sD):
-            self.sD.wait_event(ev["roi"])
-            if "before_det" in self.hooks:
-                self.hooks["before_det"](i, hp, self.sD)
-            hp.detections(self._c(self.sD))
-            if "after_det" in self.hooks:
-                self.hooks["after_det"](i, hp, self.sD)
-            hp.crops(self._c(self.sD))
-            ev["done"].record(self.sD)
+        hooks = self.hooks
+        # explicit stream handles everywhere (no stream context switches on the host)
+        hp.rpn(self._c(self.sR))
+        ev["rpn"].record(self.sR)
+        self.sA.wait_event(ev["rpn"])
+        if "before_roi" in hooks:
+            hooks["before_roi"](i, hp, self.sA)
+        hp.roi_align(self._c(self.sA))
+        ev["roi"].record(self.sA)
+        if "after_roi" in hooks:
+            hooks["after_roi"](i, hp, self.sA)
+        self.sD.wait_event(ev["roi"])
+        if "before_det" in hooks:
+            hooks["before_det"](i, hp, self.sD)
+        hp.detections(self._c(self.sD))
+        if "after_det" in hooks:
+            hooks["after_det"](i, hp, self.sD)
+        hp.crops(self._c(self.sD))
+        ev["done"].record(self.sD)
         self.k += 1
         return i
 

@@ -207,6 +207,10 @@ def test_seam_nms_sync_free_equals_compacting_version(det):
     from tests.test_mosaic_cpu import synth_tiles
     b, s, l, c, o = synth_tiles(num_tiles=6, dpi=60, seed=3)
     block = mosaic.pack_block(cu(b), cu(s), cu(l), cu(c).to(torch.int32), cu(o), 0.5, 6 * 60 + 17)
+    # mb_mosaic_pack (one launch) == the tensor-operation formulation used by the CPU/gloo host-logic tests
+    host_block = mosaic.pack_block(torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(l),
+                                   torch.from_numpy(c).to(torch.int32), torch.from_numpy(o), 0.5, 6 * 60 + 17)
+    assert torch.equal(block.cpu(), host_block)
     ref_b, ref_s, ref_l = mosaic.seam_nms(block, 0.5)
     seam = mosaic.SeamNms(block.shape[0], 3, DEV)
     seam.launch(block, 0.5)

@@ -395,6 +395,17 @@ def run_ours(args):
     roi_ms = sorted(e[0].elapsed_time(e[1]) for e in roi_ev)
     roi_mean_ms = sum(roi_ms) / len(roi_ms)
 
+    # ---- the RoIAlign launch in the other arithmetic mode (same proposals), for reference ----
+    other_exact = int(bool(args.fast_roi_align))
+    hp.roi_params.exact = other_exact
+    oev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a_, b_ in oev:
+        hp.rpn(); a_.record(); hp.roi_align(); b_.record(); hp.detections()
+    hp.roi_params.exact = 1 - other_exact
+    hp.step()
+    barrier()
+    other_ms = sorted(a_.elapsed_time(b_) for a_, b_ in oev)[len(oev) // 2]
+
     # ---- the same K batches, three in flight ----
     pipelined = None
     if plan3 is not None:
@@ -486,7 +497,10 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,
-                     "kernel_share_of_step": roi_mean_ms / ms_per_step},
+                     "kernel_share_of_step": roi_mean_ms / ms_per_step,
+                     "limiter": "L2->SM bandwidth (1.4 GB per launch of L1 misses at ~10 TB/s), see DESIGN.md section 7",
+                     "other_mode": {"mode": "exact" if other_exact else "fast(fma)", "kernel_ms": other_ms,
+                                    "frac": alg_bytes / (other_ms * 1e-3) / 1e9 / peak}},
         "stage_ms": serial_stage_ms, "host_enqueue_ms_per_step": host_ms, "pipelined": pipelined,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps,

@@ -709,6 +709,17 @@ constexpr int kChunk4 = 128;   // channels per pass of the 16-byte-gather kernel
 // weight x value products in the reference order, fed from shared registers — so EXACT stays
 // bit-identical. The kernel is bound by L1 wavefronts (profiles/), which is what this removes.
 // ------------------------------------------------------------------------------------------
+// Packed fp32x2 multiply with explicit round-to-nearest (sm_100 FMUL2). The additions of the exact mode stay
+// scalar on purpose: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad false (it
+// does honour the rounding modifiers of scalar adds), and a contracted sum is not the reference's arithmetic.
+// (Packed ops do not raise FP32 throughput here — an FMUL2 occupies the pipe like two FMULs — they only save
+// issue slots; a fully packed exact variant via doubled weights and fma(p', 0.5, t) measured no faster.)
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return reinterpret_cast<float2&>(d);
+}
+
 template <bool EXACT, int PY, int PX>
 __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const uint4 ro4, const uint4 co4,
                                             const float4* __restrict__ tw) {
@@ -719,33 +730,37 @@ __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const u
     for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int c = 0; c < NC; ++c) G[r][c] = __ldg(reinterpret_cast<const float4*>(gp + (ro[r] + co[c])));
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // Packed fp32x2 arithmetic (sm_100 FMUL2 / FFMA2): channels (0,1) and (2,3) of the 16-byte vector share one
+    // instruction; every lane of a packed multiply is rounded to nearest exactly like the scalar operation.
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
     for (int smp = 0; smp < 4; ++smp) {
         const int iy = smp >> 1, ix = smp & 1;
         const int yl = iy == 0 ? 0 : (PY == 0 ? 0 : (PY == 1 ? 1 : 2)), yh = iy == 0 ? 1 : (PY == 0 ? 1 : (PY == 1 ? 2 : 3));
         const int xl = ix == 0 ? 0 : (PX == 0 ? 0 : (PX == 1 ? 1 : 2)), xh = ix == 0 ? 1 : (PX == 0 ? 1 : (PX == 1 ? 2 : 3));
-        const float4 wv = tw[smp];
+        const float4 wa = tw[2 * smp], wb = tw[2 * smp + 1];          // (w1, w1, w2, w2), (w3, w3, w4, w4)
+        const float2 w1 = make_float2(wa.x, wa.y), w2 = make_float2(wa.z, wa.w);
+        const float2 w3 = make_float2(wb.x, wb.y), w4 = make_float2(wb.z, wb.w);
         const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
         if (EXACT) {
-#define MB_TAPSUM(acc, f)                                                                           \
-    {                                                                                               \
-        float t = __fmul_rn(wv.x, v1.f);                                                            \
-        t = __fadd_rn(t, __fmul_rn(wv.y, v2.f));                                                    \
-        t = __fadd_rn(t, __fmul_rn(wv.z, v3.f));                                                    \
-        t = __fadd_rn(t, __fmul_rn(wv.w, v4.f));                                                    \
-        acc = __fadd_rn(acc, t);                                                                    \
-    }
-            MB_TAPSUM(a0, x) MB_TAPSUM(a1, y) MB_TAPSUM(a2, z) MB_TAPSUM(a3, w)
-#undef MB_TAPSUM
+            const float2 p1 = mul2_rn(w1, make_float2(v1.x, v1.y)), p2 = mul2_rn(w2, make_float2(v2.x, v2.y));
+            const float2 p3 = mul2_rn(w3, make_float2(v3.x, v3.y)), p4 = mul2_rn(w4, make_float2(v4.x, v4.y));
+            lo.x = __fadd_rn(lo.x, __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x));
+            lo.y = __fadd_rn(lo.y, __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y));
+            const float2 q1 = mul2_rn(w1, make_float2(v1.z, v1.w)), q2 = mul2_rn(w2, make_float2(v2.z, v2.w));
+            const float2 q3 = mul2_rn(w3, make_float2(v3.z, v3.w)), q4 = mul2_rn(w4, make_float2(v4.z, v4.w));
+            hi.x = __fadd_rn(hi.x, __fadd_rn(__fadd_rn(__fadd_rn(q1.x, q2.x), q3.x), q4.x));
+            hi.y = __fadd_rn(hi.y, __fadd_rn(__fadd_rn(__fadd_rn(q1.y, q2.y), q3.y), q4.y));
         } else {
-            a0 = fmaf(wv.x, v1.x, fmaf(wv.y, v2.x, fmaf(wv.z, v3.x, fmaf(wv.w, v4.x, a0))));
-            a1 = fmaf(wv.x, v1.y, fmaf(wv.y, v2.y, fmaf(wv.z, v3.y, fmaf(wv.w, v4.y, a1))));
-            a2 = fmaf(wv.x, v1.z, fmaf(wv.y, v2.z, fmaf(wv.z, v3.z, fmaf(wv.w, v4.z, a2))));
-            a3 = fmaf(wv.x, v1.w, fmaf(wv.y, v2.w, fmaf(wv.z, v3.w, fmaf(wv.w, v4.w, a3))));
+            lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
+                 __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), lo))));
+            hi = __ffma2_rn(w1, make_float2(v1.z, v1.w), __ffma2_rn(w2, make_float2(v2.z, v2.w),
+                 __ffma2_rn(w3, make_float2(v3.z, v3.w), __ffma2_rn(w4, make_float2(v4.z, v4.w), hi))));
         }
     }
-    return make_float4(__fmul_rn(a0, 0.25f), __fmul_rn(a1, 0.25f), __fmul_rn(a2, 0.25f), __fmul_rn(a3, 0.25f));
+    const float2 q = make_float2(0.25f, 0.25f);
+    lo = mul2_rn(lo, q); hi = mul2_rn(hi, q);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
 // distinct pixel indices of one bin along one axis, in the slot order the patterns expect
@@ -756,8 +771,8 @@ __device__ __forceinline__ int axis_pattern(const Tap& A, const Tap& B, int idx[
     return 2;                                                   // C: four pixels
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_roi_align_params p,
+template <bool EXACT>     // resident CTAs per SM: 3 in exact mode (80 registers, no spills), 4 in FMA mode (64) — measured best
+__global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d(const mb_roi_align_params p,
                                                                    const float* __restrict__ rois,
                                                                    float* __restrict__ out, int* __restrict__ levels_out) {
     extern __shared__ __align__(16) float smem[];
@@ -768,9 +783,10 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_ro
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
     const int opitch = nbins | 1;
+    const int obuf = (kChunk4 * opitch + 3) & ~3;                      // floats per output buffer, a multiple of 16 bytes
     float* ob = smem;                                                  // [128][opitch]
-    float4* tab_w = reinterpret_cast<float4*>(ob + ((kChunk4 * opitch + 3) & ~3));   // [nbins][4 samples]
-    int* s_bin = reinterpret_cast<int*>(tab_w + nbins * 4);            // [nbins] ph | pw << 8 | pattern << 16
+    float4* tab_w = reinterpret_cast<float4*>(ob + obuf);              // [nbins][4 samples][2]: (w1,w1,w2,w2), (w3,w3,w4,w4)
+    int* s_bin = reinterpret_cast<int*>(tab_w + nbins * 8);            // [nbins] ph | pw << 8 | pattern << 16
 
     float r[5];
     load_roi(rois, k, p, r);
@@ -803,9 +819,11 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_ro
         const int b = e >> 2, smp = e & 3;
         const int ph = b / PW, pw = b - ph * PW;
         const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
-        tab_w[e] = (Y.valid && X.valid)
-                       ? make_float4(__fmul_rn(Y.h, X.h), __fmul_rn(Y.h, X.l), __fmul_rn(Y.l, X.h), __fmul_rn(Y.l, X.l))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool ok = Y.valid && X.valid;
+        const float w1 = ok ? __fmul_rn(Y.h, X.h) : 0.f, w2 = ok ? __fmul_rn(Y.h, X.l) : 0.f;
+        const float w3 = ok ? __fmul_rn(Y.l, X.h) : 0.f, w4 = ok ? __fmul_rn(Y.l, X.l) : 0.f;
+        tab_w[2 * e] = make_float4(w1, w1, w2, w2);
+        tab_w[2 * e + 1] = make_float4(w3, w3, w4, w4);
     }
     __syncthreads();
     for (int b = tid; b < nbins; b += kRoiThreads) {
@@ -819,15 +837,23 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_ro
 #pragma unroll
     for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * opitch;
     const int nchunks = (C + kChunk4 - 1) / kChunk4;
+    // With an odd bin count the staged chunk [128][nbins] IS the output layout: it leaves through one bulk
+    // async copy (TMA, cp.async.bulk shared -> global) issued by one thread instead of LDS.128 + STG.128 by all
+    // (a third of this kernel's L1 wavefronts). One buffer: a second one costs a resident CTA and measured slower.
+    const bool bulk = opitch == nbins && ((reinterpret_cast<uintptr_t>(dst_roi) & 15) == 0) && ((kChunk4 * nbins) & 3) == 0;
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int c0 = chunk * kChunk4;
         const int nch = min(kChunk4, C - c0);
+        if (bulk && chunk > 0) {            // the previous chunk's copy must have finished reading the buffer
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+        }
         if (4 * lane < nch) {
             const char* gp = img + (size_t)(c0 + 4 * lane) * 4;
             for (int b = warp; b < nbins; b += kRoiWarps) {
                 const int info = s_bin[b];
                 const uint4 ro4 = s_ro[info & 0xff], co4 = s_co[(info >> 8) & 0xff];
-                const float4* tw = tab_w + b * 4;
+                const float4* tw = tab_w + b * 8;
                 float4 av;
                 switch (info >> 16) {      // warp-uniform
                     case 0: av = bin_dedup<EXACT, 0, 0>(gp, ro4, co4, tw); break;
@@ -845,19 +871,23 @@ __global__ void __launch_bounds__(kRoiThreads, 3) k_roi_align_nhwc4d(const mb_ro
                 o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
             }
         }
-        __syncthreads();
         float* dst = dst_roi + (size_t)c0 * nbins;
         const int total = nch * nbins;
-        if (opitch == nbins && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (total & 3) == 0) {
-            const float4* s4 = reinterpret_cast<const float4*>(ob);
-            float4* d4 = reinterpret_cast<float4*>(dst);
-            for (int i = tid; i < total / 4; i += kRoiThreads) d4[i] = s4[i];
-        } else {
-            for (int ch = warp; ch < nch; ch += kRoiWarps)
-                for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
+        if (bulk && (total & 3) == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+                             :: "l"(dst), "r"(smem_u32(ob)), "r"(total * 4) : "memory");
+            }
+            continue;
         }
+        __syncthreads();
+        for (int ch = warp; ch < nch; ch += kRoiWarps)
+            for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
         __syncthreads();   // ob is reused by the next chunk
     }
+    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the copies
 }
 
 // NCHW -> channels-last transpose of one feature map ([N][C][HW] -> [N][HW][C]), 32x32 tiles through
@@ -984,7 +1014,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         for (int l = 0; l < p.num_levels; ++l)
             small_maps = small_maps && ((unsigned long long)p.height[l] * p.width[l] * p.channels * 4ull < (1ull << 32));
         if (vec && aligned16 && nbins <= 64 && small_maps) {   // larger bins: the scalar variant keeps more CTAs resident
-            const int smemd = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 4 * 16 + nbins * 4;
+            const int smemd = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 8 * 16 + nbins * 4;
             if (p.exact) {
                 MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
                 k_roi_align_nhwc4d<true><<<(int)num_rois, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out);

@@ -470,6 +470,99 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_small(SegArr
     if (tid == 0) s.seg_kept[g] = kept;
 }
 
+// ------------------------------------------------------------------------------------
+// The same block-resolve sweep for segments of more than 4096 boxes (T > 64 words; the cross-tile seam
+// NMS of a mosaic): the tile of block b (64 rows x (T - b) words) is staged in dynamic shared memory with
+// cp.async; with two buffers the next tile streams in while the current block is resolved and OR-ed.
+// smem: removed[Tcap] + nbuf x tile[64][Tcap] words.
+// ------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_wide(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                                       unsigned long long* __restrict__ keepbits, int max_keep,
+                                                                       int Tcap, int nbuf) {
+    extern __shared__ unsigned long long wsm[];
+    __shared__ unsigned long long s_keepw;
+    unsigned long long* removed = wsm;                 // [Tcap]
+    unsigned long long* tiles = wsm + Tcap;            // [nbuf][64 * Tcap]
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = s.seg_count[g];
+    const int T = s.seg_words[g];
+    if (n == 0 || s.totals[2] != 0) { if (tid == 0) s.seg_kept[g] = 0; return; }
+    const unsigned long long* m = mask + s.mask_off[g];
+    unsigned long long* kb = keepbits + s.keep_off[g];
+    for (int w = tid; w < T; w += kSweepThreads) removed[w] = 0;
+    // asynchronous copy of block b's tile: rows 64b .. 64b+nb-1, words b .. T-1 -> dst[row * Wn + col]
+    auto stage = [&](int b, unsigned long long* dst) {
+        const int nb = min(64, n - b * 64), Wn = T - b;
+        for (int row = warp; row < nb; row += kSweepThreads / 32) {
+            const unsigned long long* src = m + (long long)(b * 64 + row) * T + b;
+            unsigned long long* d = dst + row * Wn;
+            for (int col = lane; col < Wn; col += 32) {
+                const unsigned da = (unsigned)__cvta_generic_to_shared(d + col);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(da), "l"(src + col) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(0, tiles);
+    int kept = 0;
+    for (int b = 0; b < T; ++b) {
+        const int nb = min(64, n - b * 64), Wn = T - b;
+        unsigned long long* tile = tiles + (size_t)(nbuf > 1 ? (b & 1) : 0) * 64 * Tcap;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // tile b complete and visible; buffer (b+1)&1 is free
+        if (nbuf > 1 && b + 1 < T) stage(b + 1, tiles + (size_t)((b + 1) & 1) * 64 * Tcap);
+        if (warp == 0) {
+            const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
+            unsigned long long R = removed[b] | invalid, C = 0;
+            const int t0 = lane, t1 = lane + 32;
+            const unsigned long long s0 = (t0 < nb) ? (tile[t0 * Wn] & ((1ull << t0) - 1ull)) : 0ull;
+            const unsigned long long s1 = (t1 < nb) ? (tile[t1 * Wn] & ((1ull << t1) - 1ull)) : 0ull;
+            while ((C | R) != ~0ull) {
+                const unsigned long long D = C | R;
+                bool c0 = false, r0 = false, c1 = false, r1 = false;
+                if (!((D >> t0) & 1ull)) { if (s0 & C) r0 = true; else if ((s0 & ~R) == 0ull) c0 = true; }
+                if (!((D >> t1) & 1ull)) { if (s1 & C) r1 = true; else if ((s1 & ~R) == 0ull) c1 = true; }
+                C |= (unsigned long long)__ballot_sync(0xffffffffu, c0) | ((unsigned long long)__ballot_sync(0xffffffffu, c1) << 32);
+                R |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+            }
+            unsigned long long keepw = C;
+            if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
+                int extra = kept + __popcll(keepw) - max_keep;
+                while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+            }
+            if (lane == 0) { s_keepw = keepw; kb[b] = keepw; }
+        }
+        __syncthreads();
+        const unsigned long long keepw = s_keepw;
+        kept += __popcll(keepw);
+        if (max_keep > 0 && kept >= max_keep) {
+            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
+            break;
+        }
+        // removed[b + col] |= OR of the kept rows' words: thread = (column, quarter of the rows), 64 columns per pass
+        for (int c0 = 1; c0 < Wn; c0 += kSweepThreads / 4) {
+            const int col = c0 + (tid >> 2), q = tid & 3;
+            unsigned long long acc = 0;
+            if (col < Wn) {
+                unsigned long long bits = (keepw >> (16 * q)) & 0xffffull;
+                while (bits) {
+                    const int t = __ffsll((long long)bits) - 1 + 16 * q; bits &= bits - 1;
+                    acc |= tile[t * Wn + col];
+                }
+            }
+            acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && col < Wn && acc) removed[b + col] |= acc;
+        }
+        if (nbuf == 1) {
+            __syncthreads();                               // everyone is done with the tile before it is overwritten
+            if (b + 1 < T) stage(b + 1, tiles);
+        }
+        // nbuf == 2: the barrier at the top of the next iteration orders this OR phase before block b+1's resolve
+    }
+    if (tid == 0) s.seg_kept[g] = kept;
+}
+
 // Same sweep with the segment's whole mask preloaded into shared memory by all threads at once
 // (one latency hit with maximal memory-level parallelism) — used when n * ceil(n/64) words fit.
 static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegArrays s, const unsigned long long* __restrict__ mask,
@@ -591,6 +684,18 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
         k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);
         MB_LAUNCH_CHECK();
         return MB_OK;
+    }
+    {   // wide tiled sweep: removed[] + one or two 64-row tiles in dynamic shared memory
+        const int Tcap = ceil_div(max_seg_elems, 64);
+        const long long one = ((long long)Tcap + 64ll * Tcap) * 8, two = ((long long)Tcap + 128ll * Tcap) * 8;
+        const int nbuf = two <= 200 * 1024 ? 2 : 1;
+        const long long bytes = nbuf == 2 ? two : one;
+        if (bytes <= 200 * 1024) {
+            MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_nms_sweep_wide<<<G, kSweepThreads, (int)bytes, stream>>>(s, mask, keepbits, max_keep, Tcap, nbuf);
+            MB_LAUNCH_CHECK();
+            return MB_OK;
+        }
     }
     const int smem = sweep_smem_bytes(ceil_div(max_seg_elems, 64) + 1);
     if (smem > 48 * 1024) {

@@ -77,6 +77,13 @@ def test_nms_medium_stress(ops):
     b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
     s = (np.floor(rng.uniform(0, 1, n) * 4096) / 4096).astype(np.float32)
     assert np.array_equal(ops.nms(cu(b), cu(s), 0.5).cpu().numpy(), native.nms(b, s, 0.5))
+    # 4097..12k boxes in one segment: the wide tiled sweep with two cp.async tile buffers (20k above: one buffer)
+    for n2, extent in ((9001, 1024), (4100, 256)):
+        c = rng.uniform(0, extent, (n2, 2)); wh = np.exp(rng.uniform(np.log(8), np.log(128), (n2, 2)))
+        b2 = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)
+        s2 = cases.distinct_scores(rng, n2)
+        for thr in (0.3, 0.6):
+            assert np.array_equal(ops.nms(cu(b2), cu(s2), thr).cpu().numpy(), native.nms(b2, s2, thr)), (n2, thr)
     n = 30000
     c = rng.uniform(0, 2048, (n, 2)); wh = np.exp(rng.uniform(np.log(8), np.log(256), (n, 2)))
     b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(np.float32)

@@ -269,7 +269,7 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     MetaRule rule{d.C - 1, 1, p->trick_numel, w.img_max, w.seg_offset};
     k_seg_meta<<<1, 1024, 0, stream>>>(w.seg, G, 0, w.mask_words, rule);
     MB_LAUNCH_CHECK();
-    k_rank_in_segment<<<(int)ceil_div64(w.P, kRankThreads), kRankThreads, 0, stream>>>(
+    k_rank_in_segment<<<(int)ceil_div64(w.P, kRankKeys), kRankThreads, 0, stream>>>(
         w.bkey, w.bbox, w.bseg, w.seg.seg_start, w.seg.seg_count, nullptr, (int)w.P, w.skey, w.sbox);
     MB_LAUNCH_CHECK();
     rc = launch_mask_and_sweep(w.sbox, w.seg, G, d.max_props, p->nms_thresh, w.mask, w.keepbits, d.dpi, stream, w.seg_offset);

@@ -222,7 +222,7 @@ extern "C" int mb_nms(const float* boxes, const float* scores, const int64_t* gr
     k_scatter_boxes<<<grid, 256, 0, stream>>>((const float4*)boxes, scores, (const long long*)groups, K, G, mode,
                                               w.seg.seg_start, w.seg_fill, w.scalars, w.bkey, w.bbox, w.bseg);
     MB_LAUNCH_CHECK();
-    k_rank_in_segment<<<(int)ceil_div64(K, kRankThreads), kRankThreads, 0, stream>>>(
+    k_rank_in_segment<<<(int)ceil_div64(K, kRankKeys), kRankThreads, 0, stream>>>(
         w.bkey, w.bbox, w.bseg, w.seg.seg_start, w.seg.seg_count, nullptr, (int)K, w.skey, w.sbox);
     MB_LAUNCH_CHECK();
     int rc = launch_mask_and_sweep(w.sbox, w.seg, G, (int)K, iou_threshold, mask, w.keepbits, 0, stream);
@@ -243,7 +243,7 @@ extern "C" int mb_nms(const float* boxes, const float* scores, const int64_t* gr
     MB_LAUNCH_CHECK();
     // reuse bkey as the destination of the second-level rank; bseg is still needed -> kseg marks holes
     MB_CUDA(cudaMemsetAsync(w.bkey, 0, sizeof(unsigned long long) * K, stream));
-    k_rank_in_segment<<<(int)ceil_div64(K, kRankThreads), kRankThreads, 0, stream>>>(
+    k_rank_in_segment<<<(int)ceil_div64(K, kRankKeys), kRankThreads, 0, stream>>>(
         w.kkey, nullptr, w.kseg, w.seg2.seg_start, w.seg2.seg_count, nullptr, (int)K, w.bkey, nullptr);
     MB_LAUNCH_CHECK();
     k_emit_sorted<<<grid, 256, 0, stream>>>(w.seg, w.seg2, w.bkey, (long long*)keep_out, (long long*)status_out, w.scalars + 1);

@@ -163,7 +163,9 @@ static __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, in
 // Writes skey/sbox at seg_start + rank; optional per-segment box offset (trick mode).
 // ------------------------------------------------------------------------------------
 constexpr int kRankThreads = 256;
-constexpr int kRankTile = 1024;
+constexpr int kRankSplit = 8;                              // lanes that share one key, each counting every 8th candidate
+constexpr int kRankKeys = kRankThreads / kRankSplit;       // keys per CTA
+constexpr int kRankTile = 2048;
 
 static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
     const unsigned long long* __restrict__ bkey, const float4* __restrict__ bbox,
@@ -172,8 +174,8 @@ static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
     unsigned long long* __restrict__ skey, float4* __restrict__ sbox) {
     __shared__ unsigned long long tile[kRankTile];
     __shared__ int s_lo, s_hi;
-    const int tid = threadIdx.x;
-    const int p = blockIdx.x * kRankThreads + tid;
+    const int tid = threadIdx.x, sub = tid % kRankSplit;
+    const int p = blockIdx.x * kRankKeys + tid / kRankSplit;
     int g = -1, lo = 0, hi = 0;
     unsigned long long key = 0;
     if (p < P) {
@@ -182,7 +184,7 @@ static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
     }
     if (tid == 0) { s_lo = 0x7fffffff; s_hi = 0; }
     __syncthreads();
-    if (g >= 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
+    if (g >= 0 && sub == 0) { atomicMin(&s_lo, lo); atomicMax(&s_hi, hi); }
     __syncthreads();
     const int ulo = s_lo, uhi = s_hi;
     int rank = 0;
@@ -194,10 +196,12 @@ static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
         const int a = max(lo, t0) - t0, b = min(hi, t0 + tn) - t0;
         int cnt = 0;
 #pragma unroll 4
-        for (int j = a; j < b; ++j) cnt += (tile[j] < key) ? 1 : 0;
+        for (int j = a + sub; j < b; j += kRankSplit) cnt += (tile[j] < key) ? 1 : 0;   // 8 distinct words per warp read: no conflicts
         rank += cnt;
     }
-    if (g >= 0) {
+#pragma unroll
+    for (int d = 1; d < kRankSplit; d <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, d);
+    if (g >= 0 && sub == 0) {
         const int dst = lo + rank;
         skey[dst] = key;
         if (sbox != nullptr) {

@@ -235,6 +235,15 @@ int mb_mosaic_pack(const float* det_boxes, const float* det_scores, const int64_
 int mb_mosaic_unpack(const float* block, int64_t rows, float* boxes_out, float* scores_out,
                      int64_t* labels_out, mb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * paste_masks_in_image (tv:models/detection/roi_heads.py:375-501, called from
+ * GeneralizedRCNNTransform.postprocess tv:models/detection/transform.py:269-272).
+ * masks [R, 1, M, M] fp32 mask probabilities, boxes [R, 4] fp32 xyxy in image coordinates ->
+ * out [R, 1, im_h, im_w] fp32 (every element written). M + 2*padding <= 64, R <= 65535.
+ * ------------------------------------------------------------------------------------ */
+int mb_paste_masks(const float* masks, const float* boxes, int64_t num_masks, int32_t mask_side,
+                   int32_t padding, int32_t im_h, int32_t im_w, float* out, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

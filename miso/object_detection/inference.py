@@ -44,7 +44,7 @@ def _annotate(model, images_meta: List[ImageMetadata], model_labels, threshold, 
         for i0 in range(0, len(images_meta), batch_size):
             metas = images_meta[i0:i0 + batch_size]
             arrays = [read_image(m.full_path) for m in metas]
-            dev_u8 = [torch.from_numpy(a).cuda() for a in arrays]
+            dev_u8 = [torch.from_numpy(np.ascontiguousarray(a).copy() if not a.flags.writeable else a).cuda() for a in arrays]
             images_cuda = [a.permute(2, 0, 1).to(torch.float32) / 255 for a in dev_u8]       # ToTensor
             results = model(images_cuda)
             cap = max(max(int(r["boxes"].shape[0]) for r in results), 1)

@@ -97,6 +97,7 @@ SIGNATURES = {
     "mb_crop_gather": (C.c_int, [C.POINTER(CropParams), _p, _p, _p, _p, _p, _i64, _p]),
     "mb_mosaic_pack": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, C.c_float, _i64, _p, _p]),
     "mb_mosaic_unpack": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "mb_paste_masks": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
 }
 
 _lib = None

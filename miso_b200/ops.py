@@ -230,6 +230,26 @@ def resize_boxes(boxes: Tensor, original_size: Sequence[int], new_size: Sequence
     return out
 
 
+def paste_masks_in_image(masks: Tensor, boxes: Tensor, img_shape: Tuple[int, int], padding: int = 1) -> Tensor:
+    """tv:models/detection/roi_heads.py:490-501 — [R, 1, M, M] mask probabilities + [R, 4] boxes (image
+    coordinates) -> [R, 1, H, W] fp32: every mask padded, bilinearly resized to its (expanded, integer)
+    box and pasted into a zero image. One launch instead of a Python loop per detection."""
+    _require_cuda(masks, "masks")
+    _require_cuda(boxes, "boxes")
+    torch._assert(masks.dim() == 4 and masks.shape[1] == 1 and masks.shape[2] == masks.shape[3],
+                  f"masks should be [R, 1, M, M], got {tuple(masks.shape)}")
+    torch._assert(boxes.dim() == 2 and boxes.shape[1] == 4 and boxes.shape[0] == masks.shape[0], "boxes should be [R, 4]")
+    im_h, im_w = int(img_shape[0]), int(img_shape[1])
+    r, m = int(masks.shape[0]), int(masks.shape[-1])
+    out = torch.empty((r, 1, im_h, im_w), dtype=torch.float32, device=masks.device)
+    if r == 0:
+        return out.to(masks.dtype)
+    mk, bx = _f32c(masks), _f32c(boxes)
+    rc = _lib.load().mb_paste_masks(_ptr(mk), _ptr(bx), r, m, int(padding), im_h, im_w, _ptr(out), _stream(masks))
+    _lib.check(rc, "mb_paste_masks")
+    return out.to(masks.dtype)
+
+
 def base_anchors(scales: Sequence[float], aspect_ratios: Sequence[float]) -> Tensor:
     """AnchorGenerator.generate_anchors (tv:models/detection/anchor_utils.py:58-74), host side."""
     scales_t = torch.as_tensor(scales, dtype=torch.float32)

@@ -10,6 +10,7 @@ needs autograd, the matcher and the samplers):
     model.rpn.forward                       anchors + decode + filter_proposals      -> mb_rpn_proposals
     model.roi_heads.box_roi_pool / mask_roi_pool   MultiScaleRoIAlign                -> mb_multiscale_roi_align
     model.roi_heads.postprocess_detections  softmax/decode/clip/filters/NMS/top-k    -> mb_det_postprocess
+    model.transform.postprocess             resize_boxes + paste_masks_in_image      -> mb_resize_boxes, mb_paste_masks
 Hyper-parameters are read from the model instance at call time, never hard-coded.
 """
 from __future__ import annotations
@@ -58,6 +59,24 @@ def _postprocess_detections(self, class_logits: Tensor, box_regression: Tensor, 
     return boxes, scores, labels
 
 
+def _transform_postprocess(self, result, image_shapes, original_image_sizes):
+    """GeneralizedRCNNTransform.postprocess (tv:models/detection/transform.py:257-277)."""
+    if self.training:
+        return result
+    for i, (pred, im_s, o_im_s) in enumerate(zip(result, image_shapes, original_image_sizes)):
+        boxes = pred["boxes"]
+        if not boxes.is_cuda:
+            return self._miso_b200_orig_postprocess(result, image_shapes, original_image_sizes)
+        boxes = ops.resize_boxes(boxes, im_s, o_im_s)
+        result[i]["boxes"] = boxes
+        if "masks" in pred:
+            result[i]["masks"] = ops.paste_masks_in_image(pred["masks"], boxes, o_im_s)
+        if "keypoints" in pred:
+            from torchvision.models.detection.transform import resize_keypoints
+            result[i]["keypoints"] = resize_keypoints(pred["keypoints"], im_s, o_im_s)
+    return result
+
+
 def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu"):
     """Swap the post-head stages of a torchvision FasterRCNN / MaskRCNN instance for the CUDA
     path. strategy_rule picks which of torchvision's batched_nms switch-over rules the fused
@@ -78,6 +97,9 @@ def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu")
     if getattr(heads, "mask_roi_pool", None) is not None:
         heads._miso_b200_orig_mask_roi_pool = heads.mask_roi_pool
         heads.mask_roi_pool = ops.MultiScaleRoIAlign.from_torchvision(heads.mask_roi_pool, exact=exact_roi_align)
+    tr = model.transform
+    tr._miso_b200_orig_postprocess = tr.postprocess
+    tr.postprocess = types.MethodType(_transform_postprocess, tr)
     model._miso_b200_patched = True
     return model
 
@@ -91,6 +113,8 @@ def unpatch_model(model):
     h.box_roi_pool = h._miso_b200_orig_box_roi_pool
     if hasattr(h, "_miso_b200_orig_mask_roi_pool"):
         h.mask_roi_pool = h._miso_b200_orig_mask_roi_pool
+    if hasattr(model.transform, "_miso_b200_orig_postprocess"):
+        model.transform.postprocess = model.transform._miso_b200_orig_postprocess
     model._miso_b200_patched = False
     return model
 

@@ -315,3 +315,63 @@ def resize_boxes(boxes, original_size, new_size) -> np.ndarray:
     rh = F(F(new_size[0]) / F(original_size[0]))
     rw = F(F(new_size[1]) / F(original_size[1]))
     return np.stack([b[:, 0] * rw, b[:, 1] * rh, b[:, 2] * rw, b[:, 3] * rh], axis=1).astype(F)
+
+
+def _fma32(a, b, c) -> np.ndarray:
+    """fp32 fused multiply-add (the product of two fp32 numbers is exact in fp64; one extra rounding to fp32)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def _upsample_axis(in_size: int, out_size: int):
+    """ATen area_pixel_compute_source_index + guard_index_and_lambda for align_corners=False
+    (aten/src/ATen/native/UpSample.h), fp32, with the scale*(i+0.5)-0.5 contraction the CPU build applies."""
+    f = np.float32
+    scale = f(in_size) / f(out_size)
+    i = np.arange(out_size, dtype=f)
+    src = _fma32(scale, i + f(0.5), f(-0.5))
+    src = np.where(src < 0, f(0), src).astype(f)
+    i0 = np.minimum(src.astype(np.int64), in_size - 1)
+    lam = np.clip(src - i0.astype(f), f(0), f(1)).astype(f)
+    i1 = i0 + (i0 < in_size - 1)
+    return i0, i1, (f(1) - lam).astype(f), lam
+
+
+def interpolate_bilinear(mask, out_h: int, out_w: int) -> np.ndarray:
+    """F.interpolate(mask[None, None], size=(h, w), mode="bilinear", align_corners=False) on the CPU
+    (aten/src/ATen/native/cpu/UpSampleKernel.cpp, generic 2-d linear kernel, FMA-contracted build)."""
+    m = np.asarray(mask, np.float32)
+    y0, y1, wy0, wy1 = _upsample_axis(m.shape[0], out_h)
+    x0, x1, wx0, wx1 = _upsample_axis(m.shape[1], out_w)
+    r0, r1 = m[y0], m[y1]
+    t0 = _fma32(r0[:, x0], wx0[None, :], (r0[:, x1] * wx1[None, :]).astype(np.float32))
+    t1 = _fma32(r1[:, x0], wx0[None, :], (r1[:, x1] * wx1[None, :]).astype(np.float32))
+    return _fma32(t0, wy0[:, None], (t1 * wy1[:, None]).astype(np.float32))
+
+
+def paste_masks_in_image(masks, boxes, img_shape, padding: int = 1) -> np.ndarray:
+    """tv:models/detection/roi_heads.py:375-501: expand_masks, expand_boxes (fp32) -> int64, per detection
+    bilinear resize to (h, w) = box size (+1, at least 1) and paste into a zero image."""
+    f = np.float32
+    masks = np.asarray(masks, f)
+    boxes = np.asarray(boxes, f)
+    r, m = masks.shape[0], masks.shape[-1]
+    im_h, im_w = int(img_shape[0]), int(img_shape[1])
+    scale = f(float(m + 2 * padding) / m)
+    padded = np.pad(masks[:, 0], ((0, 0), (padding, padding), (padding, padding)))
+    w_half = ((boxes[:, 2] - boxes[:, 0]) * f(0.5)).astype(f) * scale
+    h_half = ((boxes[:, 3] - boxes[:, 1]) * f(0.5)).astype(f) * scale
+    x_c = ((boxes[:, 2] + boxes[:, 0]) * f(0.5)).astype(f)
+    y_c = ((boxes[:, 3] + boxes[:, 1]) * f(0.5)).astype(f)
+    exp = np.stack([x_c - w_half, y_c - h_half, x_c + w_half, y_c + h_half], axis=1).astype(f)
+    ib = np.trunc(exp).astype(np.int64)
+    out = np.zeros((r, 1, im_h, im_w), f)
+    for i in range(r):
+        bx0, by0, bx1, by1 = (int(v) for v in ib[i])
+        w, h = max(bx1 - bx0 + 1, 1), max(by1 - by0 + 1, 1)
+        x_0, x_1 = max(bx0, 0), min(bx1 + 1, im_w)
+        y_0, y_1 = max(by0, 0), min(by1 + 1, im_h)
+        if x_1 <= x_0 or y_1 <= y_0:
+            continue
+        resized = interpolate_bilinear(padded[i], h, w)
+        out[i, 0, y_0:y_1, x_0:x_1] = resized[y_0 - by0:y_1 - by0, x_0 - bx0:x_1 - bx0]
+    return out

@@ -175,3 +175,21 @@ def box_rel_err(a, b):
         return 0.0
     denom = np.maximum(np.abs(b).max(axis=1, keepdims=True), 1.0)
     return float(np.max(np.abs(a - b) / denom))
+
+
+def paste_case(seed=41, r=14, image_hw=(120, 150), side=28):
+    """Mask probabilities + detection boxes for paste_masks_in_image: ordinary, tiny, sub-pixel, whole
+    image, past the right/bottom edge, negative start (all intersect the image, as detections do after
+    clipping — the reference itself fails on a box entirely outside the image)."""
+    rng = np.random.default_rng(seed)
+    h, w = image_hw
+    masks = rng.random((r, 1, side, side)).astype(F)
+    c = rng.uniform(0, [w, h], (r, 2)); wh = np.exp(rng.uniform(np.log(2), np.log(110), (r, 2)))
+    b = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(F)
+    b[0] = [5, 5, 5, 5]
+    b[1] = [0, 0, w, h]
+    b[2] = [w - 3, h - 3, w + 40, h + 50]
+    b[3] = [10.6, 20.4, 10.9, 20.7]
+    b[4] = [-30, -12, 40, 33]
+    b[5] = [20.5, 30.5, 90.49, 100.51]
+    return masks, b, image_hw

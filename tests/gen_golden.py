@@ -159,7 +159,14 @@ def gen_crop():
              pixels=np.concatenate(pix) if pix else np.zeros(0, np.uint8))
 
 
+def gen_paste():
+    from torchvision.models.detection.roi_heads import paste_masks_in_image
+    masks, boxes, hw = cases.paste_case()
+    out = paste_masks_in_image(T(masks), T(boxes), hw, padding=1).numpy()
+    save("paste_masks", out=out)
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(4)
-    gen_nms(); gen_roi_align(); gen_boxes(); gen_rpn(); gen_det(); gen_crop()
+    gen_nms(); gen_roi_align(); gen_boxes(); gen_rpn(); gen_det(); gen_crop(); gen_paste()

@@ -72,12 +72,30 @@ def test_patched_model_matches_reference_stage_by_stage(kind):
         cap["pool_in"] = ({k: v.detach().cpu() for k, v in inp[0].items()}, [b.detach().cpu() for b in inp[1]], list(inp[2]))
         cap["pool_out"] = out.detach().cpu()
     h2 = box_pool.register_forward_hook(pool_hook)
+    if kind == "mask":      # capture the per-image mask probabilities that reach transform.postprocess
+        patched_tp = model.transform.postprocess
+
+        def spy_tp(result, image_shapes, original_image_sizes):
+            cap["mask_probs"] = [r["masks"].detach().cpu().clone() for r in result]
+            return patched_tp(result, image_shapes, original_image_sizes)
+        model.transform.postprocess = spy_tp
     with torch.inference_mode():
         out = model(imgs)
     h1.remove(); h2.remove()
     assert len(out) == len(imgs) and set(out[0]) >= {"boxes", "labels", "scores"}
     if kind == "mask":
         assert out[0]["masks"].shape[-2:] == imgs[0].shape[-2:]
+        # mb_paste_masks inside the patched transform.postprocess against torchvision's CPU paste on the same
+        # (captured) 28x28 mask probabilities and final boxes
+        from torchvision.models.detection.roi_heads import paste_masks_in_image as tv_paste
+        for i, o in enumerate(out):
+            if len(o["boxes"]) == 0:
+                continue
+            ref_m = tv_paste(cap["mask_probs"][i], o["boxes"].cpu(), tuple(imgs[i].shape[-2:]))
+            got_m = o["masks"].cpu()
+            assert got_m.shape == ref_m.shape
+            assert torch.equal(got_m != 0, ref_m != 0)
+            assert float((got_m - ref_m).abs().max()) <= 2.4e-7
 
     # ---- reference CPU code on the captured inputs ----
     cpu = make_model(kind)          # same seed -> same hyper-parameters (weights are irrelevant here)

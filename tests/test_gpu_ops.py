@@ -248,3 +248,32 @@ def test_roi_align_separable_fast_mode_channels_last(ops):
         ref = D.multiscale_roi_align(feats, boxes, shapes, P, 2)
         fmax = max(float(np.abs(f).max()) for f in feats)
         assert np.all(np.abs(fast - ref) <= 1e-5 * np.abs(ref) + 1e-5 * fmax), P
+
+
+def test_paste_masks_in_image(ops, golden_dir):
+    """mb_paste_masks against the golden torchvision output and the oracle: same pixels written, values
+    within 2 ulp (see tests/test_oracle_pin.py::test_paste_masks_golden); plus properties at full size."""
+    g = load(golden_dir, "paste_masks")
+    masks, boxes, hw = cases.paste_case()
+    out = ops.paste_masks_in_image(cu(masks), cu(boxes), hw).cpu().numpy()
+    assert out.shape == g["out"].shape and out.dtype == np.float32
+    assert np.array_equal(out != 0, g["out"] != 0)
+    assert np.max(np.abs(out - g["out"])) <= 2.4e-7
+    ref = D.paste_masks_in_image(masks, boxes, hw)
+    assert np.array_equal(out, ref)                       # same arithmetic as the oracle: bit-identical
+    # odd width (scalar store path), other mask size / padding, empty input, box outside the image -> zeros
+    m2 = np.random.default_rng(1).random((5, 1, 14, 14)).astype(np.float32)
+    b2 = np.array([[3, 4, 60, 70], [0, 0, 10, 10], [50, 50, 101, 99], [-40, -40, -5, -5], [20.2, 30.7, 25.1, 90.3]], np.float32)
+    o2 = ops.paste_masks_in_image(cu(m2), cu(b2), (99, 101), padding=2).cpu().numpy()
+    keep = [0, 1, 2, 4]
+    assert np.array_equal(o2[keep], D.paste_masks_in_image(m2[keep], b2[keep], (99, 101), padding=2))
+    assert not o2[3].any()
+    assert ops.paste_masks_in_image(torch.zeros((0, 1, 28, 28), device=DEV), torch.zeros((0, 4), device=DEV), (64, 64)).shape == (0, 1, 64, 64)
+    # full size: 100 masks into 1024^2 (419 MB): values in [0, 1], nothing outside the expanded integer boxes
+    rng = np.random.default_rng(2)
+    mk = torch.rand((100, 1, 28, 28), device=DEV)
+    bx = cu(cases.stress_rois(rng, 100, (1024, 1024), side=(16.0, 400.0)))
+    big = ops.paste_masks_in_image(mk, bx, (1024, 1024))
+    assert big.shape == (100, 1, 1024, 1024) and float(big.min()) >= 0.0 and float(big.max()) <= 1.0
+    sub = big[:8].cpu().numpy()
+    assert np.array_equal(sub, D.paste_masks_in_image(mk[:8].cpu().numpy(), bx[:8].cpu().numpy(), (1024, 1024)))

@@ -244,6 +244,23 @@ int mb_mosaic_unpack(const float* block, int64_t rows, float* boxes_out, float* 
 int mb_paste_masks(const float* masks, const float* boxes, int64_t num_masks, int32_t mask_side,
                    int32_t padding, int32_t im_h, int32_t im_w, float* out, mb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Input transform: ToTensor (ref:miso/object_detection/inference.py:117) +
+ * GeneralizedRCNNTransform.normalize / resize / batch_images
+ * (tv:models/detection/transform.py:165-173, 175-201 with _resize_image_and_masks :23-70, 231-255)
+ * for uint8 HWC images on the device. The caller computes the resized sizes out_h/out_w like the
+ * reference (fp32 scale factor, floor) and the padded batch size; out is [N, channels, pad_h, pad_w]
+ * fp32, every element written (zeros outside each image's out_h x out_w).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t num_images, channels;           /* channels <= 4 */
+    const uint8_t* images[MB_MAX_IMAGES];   /* device, HWC uint8, dense */
+    int32_t in_h[MB_MAX_IMAGES], in_w[MB_MAX_IMAGES], out_h[MB_MAX_IMAGES], out_w[MB_MAX_IMAGES];
+    float mean[4], std[4];
+    int32_t pad_h, pad_w;
+} mb_transform_params;
+int mb_image_transform(const mb_transform_params* params_host, float* out, mb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ def crop_objects(project: Project, output_dir: str, relative_to=None):
         if len(image.boxes) == 0:
             continue
         im = np.asarray(Image.open(image.full_path))
-        dev = torch.from_numpy(np.ascontiguousarray(im)).cuda()
+        dev = torch.from_numpy(np.array(im, copy=True)).cuda()       # copy: PIL-backed arrays are read-only
         k = len(image.boxes)
         bounds = torch.tensor([[float(v) for v in b.bounds] for b in image.boxes], dtype=torch.float32, device="cuda")
         scores = torch.ones((1, k), dtype=torch.float32, device="cuda")

@@ -45,8 +45,12 @@ def _annotate(model, images_meta: List[ImageMetadata], model_labels, threshold, 
             metas = images_meta[i0:i0 + batch_size]
             arrays = [read_image(m.full_path) for m in metas]
             dev_u8 = [torch.from_numpy(np.ascontiguousarray(a).copy() if not a.flags.writeable else a).cuda() for a in arrays]
-            images_cuda = [a.permute(2, 0, 1).to(torch.float32) / 255 for a in dev_u8]       # ToTensor
-            results = model(images_cuda)
+            if getattr(model, "_miso_b200_patched", False) and all(a.dim() == 3 and a.shape[2] == 3 for a in dev_u8):
+                from miso_b200.patch import forward_uint8
+                results = forward_uint8(model, dev_u8)       # ToTensor + model.transform fused into one kernel
+            else:
+                images_cuda = [a.permute(2, 0, 1).to(torch.float32) / 255 for a in dev_u8]       # ToTensor
+                results = model(images_cuda)
             cap = max(max(int(r["boxes"].shape[0]) for r in results), 1)
             n = len(results)
             boxes = torch.zeros((n, cap, 4), dtype=torch.float32, device="cuda")

@@ -76,6 +76,12 @@ class CropParams(C.Structure):
 
 
 # symbol -> (restype, argtypes); tests/test_abi.py checks this table against include/misob200.h
+class TransformParams(C.Structure):     # mirrors mb_transform_params
+    _fields_ = [("num_images", _i32), ("channels", _i32), ("images", C.c_void_p * 64),
+                ("in_h", _i32 * 64), ("in_w", _i32 * 64), ("out_h", _i32 * 64), ("out_w", _i32 * 64),
+                ("mean", _f32 * 4), ("std", _f32 * 4), ("pad_h", _i32), ("pad_w", _i32)]
+
+
 SIGNATURES = {
     "mb_abi_version": (C.c_int, []),
     "mb_build_info": (C.c_char_p, []),
@@ -98,6 +104,7 @@ SIGNATURES = {
     "mb_mosaic_pack": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, C.c_float, _i64, _p, _p]),
     "mb_mosaic_unpack": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
     "mb_paste_masks": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
+    "mb_image_transform": (C.c_int, [C.POINTER(TransformParams), _p, _p]),
 }
 
 _lib = None

@@ -250,6 +250,44 @@ def paste_masks_in_image(masks: Tensor, boxes: Tensor, img_shape: Tuple[int, int
     return out.to(masks.dtype)
 
 
+def resized_image_size(h: int, w: int, min_size: int, max_size: int) -> Tuple[int, int]:
+    """Output size of GeneralizedRCNNTransform.resize in eval mode (tv:models/detection/transform.py:23-70):
+    scale factor = min(min_size / min(h, w), max_size / max(h, w)), then F.interpolate(recompute_scale_factor=
+    True): floor(size * scale_factor), all in Python floats."""
+    # eager (non-scripted) torchvision 0.26 computes the factor with Python ints/floats (double precision)
+    sf = min(float(min_size) / min(h, w), float(max_size) / max(h, w))
+    return int(math.floor(float(h) * sf)), int(math.floor(float(w) * sf))
+
+
+def transform_images(images_u8: Sequence[Tensor], min_size: int, max_size: int, image_mean: Sequence[float],
+                     image_std: Sequence[float], size_divisible: int = 32) -> Tuple[Tensor, List[Tuple[int, int]]]:
+    """ToTensor + GeneralizedRCNNTransform.forward (normalize, bilinear resize, zero-padded batch) for uint8
+    HWC CUDA images in ONE launch. Returns (batch [N, C, H_pad, W_pad] fp32, resized image sizes) — the
+    fields of the reference's ImageList."""
+    torch._assert(len(images_u8) > 0, "transform_images: at least one image")
+    n, c = len(images_u8), int(images_u8[0].shape[2])
+    p = _lib.TransformParams()
+    p.num_images, p.channels = n, c
+    sizes, keep = [], []
+    for i, im in enumerate(images_u8):
+        _require_cuda(im, "images")
+        torch._assert(im.dtype == torch.uint8 and im.dim() == 3 and im.shape[2] == c, "uint8 HWC images expected")
+        imc = im.contiguous()
+        keep.append(imc)
+        h, w = int(im.shape[0]), int(im.shape[1])
+        oh, ow = resized_image_size(h, w, min_size, max_size)
+        p.images[i], p.in_h[i], p.in_w[i], p.out_h[i], p.out_w[i] = imc.data_ptr(), h, w, oh, ow
+        sizes.append((oh, ow))
+    for j in range(c):
+        p.mean[j], p.std[j] = float(image_mean[j]), float(image_std[j])
+    d = float(size_divisible)
+    p.pad_h = int(math.ceil(max(s[0] for s in sizes) / d) * d)
+    p.pad_w = int(math.ceil(max(s[1] for s in sizes) / d) * d)
+    out = torch.empty((n, c, p.pad_h, p.pad_w), dtype=torch.float32, device=images_u8[0].device)
+    _lib.check(_lib.load().mb_image_transform(C.byref(p), _ptr(out), _stream(out)), "mb_image_transform")
+    return out, sizes
+
+
 def base_anchors(scales: Sequence[float], aspect_ratios: Sequence[float]) -> Tensor:
     """AnchorGenerator.generate_anchors (tv:models/detection/anchor_utils.py:58-74), host side."""
     scales_t = torch.as_tensor(scales, dtype=torch.float32)

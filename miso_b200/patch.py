@@ -77,6 +77,23 @@ def _transform_postprocess(self, result, image_shapes, original_image_sizes):
     return result
 
 
+def forward_uint8(model, images_u8: List[Tensor]):
+    """GeneralizedRCNN.forward (tv:models/detection/generalized_rcnn.py:47-119, eval branch) for uint8 HWC CUDA
+    images: ToTensor + normalize + resize + batch run as one kernel (ops.transform_images) instead of the
+    reference's per-image tensor operations; everything downstream is the model's own (patched) code."""
+    from torchvision.models.detection.image_list import ImageList
+    tr = model.transform
+    original_image_sizes = [(int(im.shape[0]), int(im.shape[1])) for im in images_u8]
+    batch, sizes = ops.transform_images(images_u8, tr.min_size[-1], tr.max_size, tr.image_mean, tr.image_std, tr.size_divisible)
+    images = ImageList(batch, sizes)
+    features = model.backbone(images.tensors)
+    if isinstance(features, Tensor):
+        features = {"0": features}
+    proposals, _ = model.rpn(images, features)
+    detections, _ = model.roi_heads(features, proposals, images.image_sizes)
+    return tr.postprocess(detections, images.image_sizes, original_image_sizes)
+
+
 def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu"):
     """Swap the post-head stages of a torchvision FasterRCNN / MaskRCNN instance for the CUDA
     path. strategy_rule picks which of torchvision's batched_nms switch-over rules the fused

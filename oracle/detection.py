@@ -375,3 +375,28 @@ def paste_masks_in_image(masks, boxes, img_shape, padding: int = 1) -> np.ndarra
         resized = interpolate_bilinear(padded[i], h, w)
         out[i, 0, y_0:y_1, x_0:x_1] = resized[y_0 - by0:y_1 - by0, x_0 - bx0:x_1 - bx0]
     return out
+
+
+def transform_images(images_u8, min_size: int, max_size: int, image_mean, image_std, size_divisible: int = 32):
+    """ToTensor (x / 255) + GeneralizedRCNNTransform.forward in eval mode (tv:models/detection/transform.py:
+    normalize :165-173, resize :175-201 via _resize_image_and_masks :23-70, batch_images :231-255) for uint8
+    HWC arrays. Returns (batch [N, C, H_pad, W_pad] fp32, resized sizes)."""
+    f = np.float32
+    mean, std = np.asarray(image_mean, f), np.asarray(image_std, f)
+    outs, sizes = [], []
+    for a in images_u8:
+        h, w = a.shape[:2]
+        # eager (non-scripted) torchvision 0.26 computes the factor with Python ints/floats (double precision)
+        sf = min(float(min_size) / min(h, w), float(max_size) / max(h, w))
+        oh, ow = int(math.floor(float(h) * sf)), int(math.floor(float(w) * sf))
+        x = (a.astype(f) / f(255)).astype(f)
+        x = ((x - mean) / std).astype(f)
+        outs.append(np.stack([interpolate_bilinear(x[..., c], oh, ow) for c in range(x.shape[2])]))
+        sizes.append((oh, ow))
+    d = float(size_divisible)
+    ph = int(math.ceil(max(s[0] for s in sizes) / d) * d)
+    pw = int(math.ceil(max(s[1] for s in sizes) / d) * d)
+    batch = np.zeros((len(outs), outs[0].shape[0], ph, pw), f)
+    for i, o in enumerate(outs):
+        batch[i, :, : o.shape[1], : o.shape[2]] = o
+    return batch, sizes

@@ -193,3 +193,11 @@ def paste_case(seed=41, r=14, image_hw=(120, 150), side=28):
     b[4] = [-30, -12, 40, 33]
     b[5] = [20.5, 30.5, 90.49, 100.51]
     return masks, b, image_hw
+
+
+def transform_case(seed=51):
+    """uint8 HWC images of different sizes for the input transform (min_size 96, max_size 150: the
+    second image is limited by max_size)."""
+    rng = np.random.default_rng(seed)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in ((60, 84), (131, 58), (77, 77))]
+    return imgs, 96, 150, [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]

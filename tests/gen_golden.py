@@ -166,7 +166,15 @@ def gen_paste():
     save("paste_masks", out=out)
 
 
+def gen_transform():
+    from torchvision.models.detection.transform import GeneralizedRCNNTransform
+    imgs, mn, mx, mean, std = cases.transform_case()
+    tr = GeneralizedRCNNTransform(mn, mx, mean, std).eval()
+    il, _ = tr([T(a).permute(2, 0, 1).to(torch.float32) / 255 for a in imgs])      # ToTensor + transform
+    save("transform", batch=il.tensors.numpy(), sizes=np.array(il.image_sizes, np.int64))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     torch.set_num_threads(4)
-    gen_nms(); gen_roi_align(); gen_boxes(); gen_rpn(); gen_det(); gen_crop(); gen_paste()
+    gen_nms(); gen_roi_align(); gen_boxes(); gen_rpn(); gen_det(); gen_crop(); gen_paste(); gen_transform()

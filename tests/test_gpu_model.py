@@ -169,6 +169,33 @@ def test_patched_model_matches_reference_stage_by_stage(kind):
         assert r > 0.9, r
 
 
+def test_forward_uint8_equals_float_forward():
+    """patch.forward_uint8 (fused ToTensor + normalize + resize + batch) feeds the backbone the same tensor,
+    bit for bit, as the reference transform on the float images — so the detections are identical."""
+    from miso_b200.patch import forward_uint8, patch_model
+    model = patch_model(make_model("faster").to(DEV))
+    g = torch.Generator().manual_seed(5)
+    u8 = [torch.randint(0, 256, (300 + 40 * i, 420 - 30 * i, 3), dtype=torch.uint8, generator=g).to(DEV) for i in range(2)]
+    with torch.inference_mode():
+        il, _ = model.transform([a.permute(2, 0, 1).to(torch.float32) / 255 for a in u8])
+        from miso_b200 import ops
+        tr = model.transform
+        batch, sizes = ops.transform_images(u8, tr.min_size[-1], tr.max_size, tr.image_mean, tr.image_std, tr.size_divisible)
+        assert sizes == [tuple(s) for s in il.image_sizes]
+        # torchvision's CUDA interpolate rounds differently from its CPU kernel; the parity target is the CPU path
+        # (tests/test_gpu_ops.py::test_transform_images is bit-exact against it), so here: close, same shape
+        assert batch.shape == il.tensors.shape and float((batch - il.tensors).abs().max()) < 1e-4
+        a = forward_uint8(model, u8)
+        # the model's own forward on the float images, with its transform handing over the same batch: everything
+        # around the transform (original sizes, backbone call, postprocess) must then agree exactly
+        from torchvision.models.detection.image_list import ImageList
+        model.transform.forward = lambda images, targets=None: (ImageList(batch, sizes), targets)
+        b = model([x.permute(2, 0, 1).to(torch.float32) / 255 for x in u8])
+        del model.transform.forward
+    for x, y in zip(a, b):
+        assert torch.equal(x["boxes"], y["boxes"]) and torch.equal(x["labels"], y["labels"]) and torch.equal(x["scores"], y["scores"])
+
+
 def test_dispatcher_override_routes_torchvision_ops():
     import torchvision
     from miso_b200.patch import override_torchvision_ops

@@ -277,3 +277,19 @@ def test_paste_masks_in_image(ops, golden_dir):
     assert big.shape == (100, 1, 1024, 1024) and float(big.min()) >= 0.0 and float(big.max()) <= 1.0
     sub = big[:8].cpu().numpy()
     assert np.array_equal(sub, D.paste_masks_in_image(mk[:8].cpu().numpy(), bx[:8].cpu().numpy(), (1024, 1024)))
+
+
+def test_transform_images(ops, golden_dir):
+    """mb_image_transform (ToTensor + normalize + bilinear resize + zero-padded batch in one launch) against
+    the torchvision golden fixture and the oracle — bit-identical — and at the BASELINE size (1024^2 -> 800^2)."""
+    g = load(golden_dir, "transform")
+    imgs, mn, mx, mean, std = cases.transform_case()
+    batch, sizes = ops.transform_images([cu(a) for a in imgs], mn, mx, mean, std)
+    assert np.array_equal(np.array(sizes), g["sizes"])
+    assert np.array_equal(batch.cpu().numpy(), g["batch"])
+    rng = np.random.default_rng(0)
+    big = [rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8) for _ in range(2)] + [rng.integers(0, 256, (700, 1000, 3), dtype=np.uint8)]
+    b2, s2 = ops.transform_images([cu(a) for a in big], 800, 1333, mean, std)
+    rb, rs = D.transform_images(big, 800, 1333, mean, std)
+    assert s2 == rs and tuple(b2.shape) == rb.shape == (3, 3, 800, 1152)
+    assert np.array_equal(b2.cpu().numpy(), rb)

@@ -405,17 +405,16 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_small(SegArr
     unsigned long long* kb = keepbits + s.keep_off[g];
     if (tid < T) removed[tid] = 0;
     unsigned long long pre[kPre];
-    // tile of block b: rows 64b .. 64b+nb-1, words b .. T-1, row-major with Wn = T - b words per row
+    // tile of block b: rows 64b .. 64b+nb-1, words b .. T-1, row-major with Wn = T - b words per row.
+    // Thread (warp, lane) owns rows warp, warp+8, .. and columns lane, lane+32: no index division, and a
+    // warp reads up to 32 consecutive words of one row.
+    static_assert(kPre == 16 && kSweepThreads == 256 && kSweepSmallMaxWords == 64, "prefetch mapping");
     auto prefetch = [&](int b) {
         const int nb = min(64, n - b * 64), Wn = T - b;
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
-            const int idx = tid + u * kSweepThreads;
-            pre[u] = 0;
-            if (idx < nb * Wn) {
-                const int row = idx / Wn, col = idx - row * Wn;
-                pre[u] = m[(long long)(b * 64 + row) * T + b + col];
-            }
+            const int row = warp + 8 * (u >> 1), col = lane + 32 * (u & 1);
+            pre[u] = (row < nb && col < Wn) ? m[(long long)(b * 64 + row) * T + b + col] : 0ull;
         }
     };
     prefetch(0);
@@ -424,8 +423,8 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_small(SegArr
         const int nb = min(64, n - b * 64), Wn = T - b;
 #pragma unroll
         for (int u = 0; u < kPre; ++u) {
-            const int idx = tid + u * kSweepThreads;
-            if (idx < nb * Wn) tile[idx] = pre[u];
+            const int row = warp + 8 * (u >> 1), col = lane + 32 * (u & 1);
+            if (row < nb && col < Wn) tile[row * Wn + col] = pre[u];
         }
         __syncthreads();
         if (b + 1 < T) prefetch(b + 1);          // global loads of the next tile fly during the resolve

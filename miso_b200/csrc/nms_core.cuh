@@ -245,7 +245,7 @@ __device__ __forceinline__ float4 offset_box(float4 b, float o) {
 
 // seg_offset (nullable): per-segment coordinate offset of the batched_nms coordinate trick,
 // added on load (tv:ops/boxes.py:101); 0 for segments that run the per-group strategy.
-static __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
+static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
                                                  float thr_up, unsigned long long* __restrict__ mask,
                                                  const float* __restrict__ seg_offset) {
     __shared__ float4 cbox[64];
@@ -282,30 +282,33 @@ static __global__ void __launch_bounds__(64) k_nms_mask(const float4* __restrict
             carea[tid] = box_area_rn(b);
         }
         __syncthreads();
-        const int row = r * 64 + tid;
+        // two threads per row: thread (row, half) tests columns 32*half .. 32*half+31 and writes its own
+        // 32-bit half of the mask word (little-endian halves of the 64-bit word)
+        const int row = r * 64 + (tid & 63), half = tid >> 6;
         if (row < n) {
             const float4 a = offset_box(sbox[st + row], off);
             const float area_a = box_area_rn(a);
-            unsigned long long word = 0;
-            // Diagonal tiles carry the full symmetric word (bits j < tid too): the sweep resolves a
+            unsigned int word = 0;
+            // Diagonal tiles carry the full symmetric word (bits j < row too): the sweep resolves a
             // 64-box block in parallel from "who suppresses me" = word & lower bits.
-            const int skip = (r == c) ? tid : -1;
+            const int skip = (r == c) ? (tid & 63) : -1;
+            const int j0 = 32 * half, j1 = min(ncol, j0 + 32);
             if (thr_up > 0.0f) {
                 // an IoU above a positive threshold needs a positive intersection: most pairs are
                 // disjoint and never reach the division
-                for (int j = 0; j < ncol; ++j) {
+                for (int j = j0; j < j1; ++j) {
                     const float4 b = cbox[j];
                     const float xx1 = (a.x < b.x) ? b.x : a.x, yy1 = (a.y < b.y) ? b.y : a.y;
                     const float xx2 = (b.z < a.z) ? b.z : a.z, yy2 = (b.w < a.w) ? b.w : a.w;
                     if (xx2 > xx1 && yy2 > yy1 && j != skip &&
                         iou_suppresses(a, area_a, b, carea[j], thr_up))
-                        word |= 1ull << j;
+                        word |= 1u << (j - j0);
                 }
             } else {
-                for (int j = 0; j < ncol; ++j)
-                    if (j != skip && iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1ull << j;
+                for (int j = j0; j < j1; ++j)
+                    if (j != skip && iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1u << (j - j0);
             }
-            mask[s.mask_off[g] + (long long)row * T + c] = word;
+            reinterpret_cast<unsigned int*>(mask)[2 * (s.mask_off[g] + (long long)row * T + c) + half] = word;
         }
         __syncthreads();
     }
@@ -671,7 +674,7 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
                                  unsigned long long* mask, unsigned long long* keepbits, int max_keep,
                                  cudaStream_t stream, const float* seg_offset = nullptr) {
     const float thr_up = strict_gt_threshold(iou_threshold);
-    k_nms_mask<<<kNumSMs * 16, 64, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
+    k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
     const long long pre_bytes = (long long)max_seg_elems * ceil_div(max_seg_elems, 64) * 8;
     // the whole-mask preload variant needs up to 160 KB of shared memory per CTA; measured slightly slower than the

@@ -86,6 +86,21 @@ def test_hot_path_is_deterministic_and_idempotent():
     assert torch.equal(pix, hp.crop_pixels[: int(hp.crop_totals[1])])
 
 
+def test_hot_path_graph_replay_equals_step():
+    w, hp = build(seed=4)
+    hp.step(); torch.cuda.synchronize()
+    want = [t.clone() for t in (hp.proposals, hp.box_features, hp.det_boxes, hp.det_labels, hp.crop_totals)]
+    pix = hp.crop_pixels[: int(hp.crop_totals[1])].clone()
+    hp.capture()
+    for t in (hp.proposals, hp.box_features, hp.det_boxes, hp.crop_pixels):
+        t.fill_(3)
+    hp.replay(); hp.replay()
+    torch.cuda.synchronize()
+    for x, y in zip(want, (hp.proposals, hp.box_features, hp.det_boxes, hp.det_labels, hp.crop_totals)):
+        assert torch.equal(x, y)
+    assert torch.equal(pix, hp.crop_pixels[: int(hp.crop_totals[1])])
+
+
 def test_hot_path_full_size_config2_properties():
     """BASELINE config 2 at full size (batch 4, 800^2, 256 ch, 1000 proposals): size-independent
     properties — proposal scores sorted, NMS idempotence (re-running NMS on the kept proposals keeps

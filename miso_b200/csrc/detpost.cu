@@ -135,12 +135,16 @@ __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev 
     if (use_merge) {
         // few classes: every class's kept list is already sorted, so merge by rank (no sort);
         // the merged order lands in keys[total .. 2*total)
+        for (int i = tid; i < S * (kSweepSmallMaxWords + 1); i += kDetFinalThreads) {   // independent loads, one latency
+            const int c = i / (kSweepSmallMaxWords + 1), q = i - c * (kSweepSmallMaxWords + 1);
+            const int g = n * S + c;
+            wpre[c][q] = (q < w.seg.seg_words[g]) ? __popcll(w.keepbits[w.seg.keep_off[g] + q]) : 0;
+        }
+        __syncthreads();
         if (tid < S) {
-            const int g = n * S + tid;
-            const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-            const int T = w.seg.seg_words[g];
+            const int T = w.seg.seg_words[n * S + tid];
             int acc = 0;
-            for (int q = 0; q < T; ++q) { wpre[tid][q] = acc; acc += __popcll(kb[q]); }
+            for (int q = 0; q < T; ++q) { const int cq = wpre[tid][q]; wpre[tid][q] = acc; acc += cq; }
             wpre[tid][T] = acc;
         }
         __syncthreads();

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
     const int nc = __ldcg(&w.n_cand[g]);
     int need = k - na;  // winners still to take from the candidates (1 <= need <= nc)
     unsigned long long prefix = 0x000fffffffffffffull;   // take every candidate unless narrowed below
+    // (sorting all candidates together with the definite picks instead of narrowing first measured slower: the
+    // bitonic sort doubles in size, the seven radix passes over a few hundred keys are cheap)
     if (nc > need) {
         // radix-select the need-th smallest candidate key over the remaining 52 bits, 8 bits per pass
         unsigned long long pmask = 0;
@@ -310,13 +312,22 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
     __shared__ int wpre[MB_MAX_LEVELS][kSweepSmallMaxWords + 1];
     const int n = blockIdx.x, tid = threadIdx.x;
     const int Ktot = d.koff[d.L];
-    // per level: exclusive popcount prefix over the keep words, and the run offsets
+    // per level: exclusive popcount prefix over the keep words, and the run offsets.
+    // One thread per (level, word) fetches and counts its word (independent loads, one latency), then one
+    // thread per level scans the counts in shared memory.
+    {
+        const int l = tid / (kSweepSmallMaxWords + 1), q = tid - l * (kSweepSmallMaxWords + 1);
+        if (l < d.L) {
+            const int g = n * d.L + l;
+            const int T = w.seg.seg_words[g];
+            wpre[l][q] = (q < T) ? __popcll(w.keepbits[w.seg.keep_off[g] + q]) : 0;
+        }
+    }
+    __syncthreads();
     if (tid < d.L) {
-        const int g = n * d.L + tid;
-        const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        const int T = w.seg.seg_words[g];
+        const int T = w.seg.seg_words[n * d.L + tid];
         int acc = 0;
-        for (int q = 0; q < T; ++q) { wpre[tid][q] = acc; acc += __popcll(kb[q]); }
+        for (int q = 0; q < T; ++q) { const int c = wpre[tid][q]; wpre[tid][q] = acc; acc += c; }
         wpre[tid][T] = acc;
     }
     __syncthreads();

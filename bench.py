@@ -278,7 +278,6 @@ def run_ours(args):
     n, dpi = args.batch, hp.dpi
     # mosaic framing for N > 1: this rank's images are tiles at (row=rank, col=i) of a tile grid with 128 px overlap
     origins = torch.tensor([[rank * 896.0, i * 896.0] for i in range(n)], dtype=torch.float32, device=dev)
-    seam = mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev) if world > 1 else None
 
     # The timed region runs one batch at a time (rpn -> roi_align -> detections -> crops, event-chained), so that
     # the RoIAlign launch durations and their share of the step are those of the kernel running alone. A second
@@ -294,11 +293,18 @@ def run_ours(args):
     plan1 = pipeline.OverlappedHotPath(hps[:1])
     plan3 = pipeline.OverlappedHotPath(hps) if len(hps) > 1 else None
 
-    comm = torch.cuda.Stream(device=dev) if world > 1 else None
-    x_block = torch.empty((n * dpi, 6), dtype=torch.float32, device=dev)             # this rank's block / all ranks' blocks
-    x_gathered = torch.empty((world * n * dpi, 6), dtype=torch.float32, device=dev)  # (reused: the comm stream is in order)
-    ev_det = [torch.cuda.Event() for _ in hps]
-    ev_pack = [None for _ in hps]
+    # Exchange plumbing (N > 1): the block is packed on the detection stream right behind mb_det_postprocess (one
+    # 3 us kernel, three rotating buffers), so the next batch never waits for the exchange; all-gather + seam NMS
+    # alternate between two communication streams with their own buffers — the seam NMS is a latency chain on a
+    # couple of CTAs, two of them in flight cost nothing and double its throughput.
+    NBLK, NCOMM = 3, 2
+    comms = [torch.cuda.Stream(device=dev) for _ in range(NCOMM)] if world > 1 else []
+    seams = [mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev) for _ in range(NCOMM)] if world > 1 else []
+    x_block = [torch.empty((n * dpi, 6), dtype=torch.float32, device=dev) for _ in range(NBLK)]
+    x_gathered = [torch.empty((world * n * dpi, 6), dtype=torch.float32, device=dev) for _ in range(NCOMM)]
+    ev_packed = [torch.cuda.Event() for _ in range(NBLK)]
+    ev_gathered = [None] * NBLK           # all-gather that last read x_block[b] has completed
+    xstep = [0]
     roi_ev = []           # (start, end) CUDA events around every RoIAlign launch of the timed region, on its stream
     recording = [False]
 
@@ -312,28 +318,30 @@ def run_ours(args):
         if recording[0]:
             roi_ev[-1][1].record(st)
 
-    def before_det(i, hp_i, st):
-        if world > 1 and ev_pack[i] is not None:
-            st.wait_event(ev_pack[i])        # the previous exchange has read this slot's detection buffers
-
     def after_det(i, hp_i, st):
-        """The path's one exchange, on its own stream so that it overlaps the following batch:
-        fixed-size blocks -> one all_gather_into_tensor -> seam NMS right behind it, no host sync."""
+        """The path's one exchange: fixed-size block -> one all_gather_into_tensor -> seam NMS right behind it,
+        no host sync anywhere."""
         if world == 1:
             return
-        ev_det[i].record(st)
-        with torch.cuda.stream(comm):
-            comm.wait_event(ev_det[i])
+        k_, b_, c_ = xstep[0], xstep[0] % NBLK, xstep[0] % NCOMM
+        xstep[0] += 1
+        if ev_gathered[b_] is not None:
+            st.wait_event(ev_gathered[b_])           # (three steps old: long done)
+        with torch.cuda.stream(st):
             mosaic.pack_block(hp_i.det_boxes, hp_i.det_scores, hp_i.det_labels, hp_i.det_counts, origins,
-                              w.threshold, n * dpi, out=x_block)
-            if ev_pack[i] is None:
-                ev_pack[i] = torch.cuda.Event()
-            ev_pack[i].record(comm)
-            seam.launch(mosaic.exchange(x_block, world, out=x_gathered), w.det.nms_thresh)
+                              w.threshold, n * dpi, out=x_block[b_])
+        ev_packed[b_].record(st)
+        with torch.cuda.stream(comms[c_]):
+            comms[c_].wait_event(ev_packed[b_])
+            g_ = mosaic.exchange(x_block[b_], world, out=x_gathered[c_])
+            if ev_gathered[b_] is None:
+                ev_gathered[b_] = torch.cuda.Event()
+            ev_gathered[b_].record(comms[c_])
+            seams[c_].launch(g_, w.det.nms_thresh)
 
     for pl in (plan1, plan3):
         if pl is not None:
-            pl.hooks.update(before_roi=before_roi, after_roi=after_roi, before_det=before_det, after_det=after_det)
+            pl.hooks.update(before_roi=before_roi, after_roi=after_roi, after_det=after_det)
     host_enqueue = [0.0]
 
     def run_steps(plan, k):
@@ -343,7 +351,8 @@ def run_ours(args):
         host_enqueue[0] = (time.perf_counter() - t_h) / k
         plan.drain()
         if world > 1:
-            torch.cuda.current_stream(dev).wait_stream(comm)     # the region ends with the last seam NMS
+            for c_ in comms:
+                torch.cuda.current_stream(dev).wait_stream(c_)   # the region ends with the last seam NMS
 
     def timed(plan, k):
         """K batches submitted and completed between two events on the current stream; max over ranks."""
@@ -431,7 +440,7 @@ def run_ours(args):
 
     # ---- e2e: host (pinned) inputs, H2D + path + D2H of results every step, through the public host-facing
     # API (pipeline.HostPipeline: copy-in / compute / copy-out streams, two slots) ----
-    seams = {}
+    e2e_seams = {}
 
     def make_hp():
         return pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=128 << 20,
@@ -440,7 +449,7 @@ def run_ours(args):
     def on_computed(hp_s, slot):
         if world == 1:
             return
-        sm_ = seams.setdefault(id(slot), mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev))
+        sm_ = e2e_seams.setdefault(id(slot), mosaic.SeamNms(world * n * dpi, w.shapes.num_classes, dev))
         block = mosaic.pack_block(hp_s.det_boxes, hp_s.det_scores, hp_s.det_labels, hp_s.det_counts, origins, w.threshold, n * dpi)
         sm_.launch(mosaic.exchange(block, world), w.det.nms_thresh)
         slot["seam_done"] = torch.cuda.Event(); slot["seam_done"].record()
@@ -449,7 +458,7 @@ def run_ours(args):
         if world == 1:
             return None
         slot["seam_done"].synchronize()
-        b, s_, l = seams[id(slot)].finish()
+        b, s_, l = e2e_seams[id(slot)].finish()
         return b.cpu(), s_.cpu(), l.cpu()
 
     pipe = pipeline.HostPipeline(make_hp, w.host, depth=2, on_computed=on_computed, on_collect=on_collect)
@@ -507,7 +516,7 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": w.name, "per_gpu_batch": args.batch, "features_layout": hp.features_layout, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
-                   "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step on a second stream (overlaps the next batch)" if world > 1 else "single GPU",
+                   "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step, alternating between two communication streams (overlap the following batches)" if world > 1 else "single GPU",
                    "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
         "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,

@@ -517,7 +517,8 @@ def run_ours(args):
         "config": {"workload": w.name, "per_gpu_batch": args.batch, "features_layout": hp.features_layout, "l2": "inputs larger than L2 (218 MB pyramid + 201 MB RoIAlign output per step)",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
                    "multi_gpu": "per-rank batch = shard of mosaic tiles; NCCL all_gather + seam NMS every step, alternating between two communication streams (overlap the following batches)" if world > 1 else "single GPU",
-                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes},
+                   "detections_per_step": total_dets, "crop_bytes_per_step": crop_bytes,
+                   "images_per_s": world * args.batch / (ms_per_step * 1e-3)},
         "roofline": {"bound": "hbm", "kernel": roi_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                      "kernel_ms_mean": roi_mean_ms, "kernel_ms_min": roi_ms[0], "rois": k_live, "touched_pixels": touched,

@@ -774,33 +774,39 @@ __device__ __forceinline__ int axis_pattern(const Tap& A, const Tap& B, int idx[
 template <bool EXACT>     // resident CTAs per SM: 3 in exact mode (80 registers, no spills), 4 in FMA mode (64) — measured best
 __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d(const mb_roi_align_params p,
                                                                    const float* __restrict__ rois,
-                                                                   float* __restrict__ out, int* __restrict__ levels_out) {
+                                                                   float* __restrict__ out, int* __restrict__ levels_out,
+                                                                   int rows_per_cta) {
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[32], xtab[32];
     __shared__ uint4 s_ro[16], s_co[16];             // byte offsets of the distinct rows / columns of each bin row / column
     __shared__ int s_py[16], s_px[16];
     const int k = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW;
-    const int opitch = nbins | 1;
+    // blockIdx.y selects a band of pooled rows (one band = the whole RoI for the 7x7 box head; the 14x14 mask
+    // head runs as two bands of 7 rows so that the staged outputs of a band still fit three CTAs per SM)
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins_all = PH * PW;
+    const int ph0 = blockIdx.y * rows_per_cta;
+    const int b0 = ph0 * PW, nbins = min(rows_per_cta, PH - ph0) * PW;     // this CTA's bins: b0 .. b0 + nbins - 1
+    const int opitch = (rows_per_cta * PW) | 1;
     const int obuf = (kChunk4 * opitch + 3) & ~3;                      // floats per output buffer, a multiple of 16 bytes
     float* ob = smem;                                                  // [128][opitch]
     float4* tab_w = reinterpret_cast<float4*>(ob + obuf);              // [nbins][4 samples][2]: (w1,w1,w2,w2), (w3,w3,w4,w4)
-    int* s_bin = reinterpret_cast<int*>(tab_w + nbins * 8);            // [nbins] ph | pw << 8 | pattern << 16
+    int* s_bin = reinterpret_cast<int*>(tab_w + rows_per_cta * PW * 8);   // [nbins] ph | pw << 8 | pattern << 16
 
     float r[5];
     load_roi(rois, k, p, r);
     RoiGeom g;
     roi_geometry(r, p, g);
-    if (levels_out != nullptr && tid == 0) levels_out[k] = g.level;
+    if (levels_out != nullptr && tid == 0 && blockIdx.y == 0) levels_out[k] = g.level;
     const int ny = PH * 2, nx = PW * 2;
     if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
     if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
     __syncthreads();
     const int C = p.channels;
-    float* dst_roi = out + (size_t)k * C * nbins;
+    float* dst_roi = out + (size_t)k * C * nbins_all;
     if (g.batch < 0 || g.batch >= p.num_images) {
-        for (long long i = tid; i < (long long)C * nbins; i += kRoiThreads) dst_roi[i] = 0.0f;
+        if (blockIdx.y == 0)
+            for (long long i = tid; i < (long long)C * nbins_all; i += kRoiThreads) dst_roi[i] = 0.0f;
         return;
     }
     if (tid < PH) {
@@ -817,7 +823,7 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
     }
     for (int e = tid; e < nbins * 4; e += kRoiThreads) {
         const int b = e >> 2, smp = e & 3;
-        const int ph = b / PW, pw = b - ph * PW;
+        const int ph = ph0 + b / PW, pw = b % PW;
         const Tap Y = ytab[ph * 2 + (smp >> 1)], X = xtab[pw * 2 + (smp & 1)];
         const bool ok = Y.valid && X.valid;
         const float w1 = ok ? __fmul_rn(Y.h, X.h) : 0.f, w2 = ok ? __fmul_rn(Y.h, X.l) : 0.f;
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
     }
     __syncthreads();
     for (int b = tid; b < nbins; b += kRoiThreads) {
-        const int ph = b / PW, pw = b - ph * PW;
+        const int ph = ph0 + b / PW, pw = b % PW;
         s_bin[b] = ph | (pw << 8) | ((s_py[ph] * 3 + s_px[pw]) << 16);
     }
     __syncthreads();
@@ -840,7 +846,8 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
     // With an odd bin count the staged chunk [128][nbins] IS the output layout: it leaves through one bulk
     // async copy (TMA, cp.async.bulk shared -> global) issued by one thread instead of LDS.128 + STG.128 by all
     // (a third of this kernel's L1 wavefronts). One buffer: a second one costs a resident CTA and measured slower.
-    const bool bulk = opitch == nbins && ((reinterpret_cast<uintptr_t>(dst_roi) & 15) == 0) && ((kChunk4 * nbins) & 3) == 0;
+    const bool bulk = gridDim.y == 1 && opitch == nbins && ((reinterpret_cast<uintptr_t>(dst_roi) & 15) == 0) &&
+                      ((kChunk4 * nbins) & 3) == 0;
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int c0 = chunk * kChunk4;
         const int nch = min(kChunk4, C - c0);
@@ -871,7 +878,7 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
                 o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
             }
         }
-        float* dst = dst_roi + (size_t)c0 * nbins;
+        float* dst = dst_roi + (size_t)c0 * nbins_all + b0;
         const int total = nch * nbins;
         if (bulk && (total & 3) == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
@@ -884,7 +891,7 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
         }
         __syncthreads();
         for (int ch = warp; ch < nch; ch += kRoiWarps)
-            for (int b = lane; b < nbins; b += 32) dst[ch * nbins + b] = ob[ch * opitch + b];
+            for (int b = lane; b < nbins; b += 32) dst[ch * nbins_all + b] = ob[ch * opitch + b];
         __syncthreads();   // ob is reused by the next chunk
     }
     if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the copies
@@ -1013,14 +1020,19 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         bool small_maps = true;   // 32-bit byte offsets inside one image
         for (int l = 0; l < p.num_levels; ++l)
             small_maps = small_maps && ((unsigned long long)p.height[l] * p.width[l] * p.channels * 4ull < (1ull << 32));
-        if (vec && aligned16 && nbins <= 64 && small_maps) {   // larger bins: the scalar variant keeps more CTAs resident
-            const int smemd = ((kChunk4 * (nbins | 1) + 3) & ~3) * (int)sizeof(float) + nbins * 8 * 16 + nbins * 4;
+        if (vec && aligned16 && small_maps) {
+            // bands of pooled rows per CTA: at most 112 bins staged at a time (7x7: one band; 14x14: two bands of 7 rows)
+            const int nsplit = ceil_div(nbins, 112);
+            const int rows = ceil_div(p.pooled_h, nsplit);
+            const int band = rows * p.pooled_w;
+            const int smemd = ((kChunk4 * (band | 1) + 3) & ~3) * (int)sizeof(float) + band * 8 * 16 + band * 4;
+            dim3 grid((unsigned)num_rois, (unsigned)ceil_div(p.pooled_h, rows));
             if (p.exact) {
                 MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
-                k_roi_align_nhwc4d<true><<<(int)num_rois, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out);
+                k_roi_align_nhwc4d<true><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows);
             } else {
                 MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
-                k_roi_align_nhwc4d<false><<<(int)num_rois, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out);
+                k_roi_align_nhwc4d<false><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows);
             }
             MB_LAUNCH_CHECK();
             return MB_OK;

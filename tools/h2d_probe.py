@@ -1,0 +1,16 @@
+"""Pinned host -> device copy rate of this box with 1/2/4 copy streams (context for the e2e number: 243 MB per batch)."""
+import torch, time
+x = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+d = torch.empty_like(x, device="cuda")
+for n in (1, 2, 4):
+    streams = [torch.cuda.Stream() for _ in range(n)]
+    chunk = x.numel() // n
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        for i, s in enumerate(streams):
+            with torch.cuda.stream(s):
+                d[i * chunk:(i + 1) * chunk].copy_(x[i * chunk:(i + 1) * chunk], non_blocking=True)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 10
+    print(f"{n} stream(s): {x.numel() / dt / 1e9:.1f} GB/s")

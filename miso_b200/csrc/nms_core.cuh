@@ -320,65 +320,74 @@ static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restric
 // (later boxes of the segment all score lower, so they cannot enter a global top-max_keep).
 // ------------------------------------------------------------------------------------
 constexpr int kSweepThreads = 256;
+constexpr int kSweepBigThreads = 1024;
 
-static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep(SegArrays s, const unsigned long long* __restrict__ mask,
-                                                            unsigned long long* __restrict__ keepbits, int max_keep) {
+// Generic sweep for segments of any size (the mask rows do not fit in shared memory): per 64-box block, one warp
+// resolves the block from its diagonal words (parallel fixed point, see k_nms_sweep_small), then the kept rows are
+// streamed from global memory one row per warp — every lane issues its whole strided share of the row before the
+// first use, so a row costs one memory latency — and OR-ed into removed[] (shared memory, T words).
+static __global__ void __launch_bounds__(kSweepBigThreads) k_nms_sweep(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                                     unsigned long long* __restrict__ keepbits, int max_keep) {
     extern __shared__ unsigned long long removed[];
     __shared__ unsigned long long diag[64];
-    const int g = blockIdx.x, tid = threadIdx.x;
+    __shared__ unsigned long long s_keepw;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int kWarps = kSweepBigThreads / 32;
     const int n = s.seg_count[g];
     const int T = s.seg_words[g];
     const bool overflow = s.totals[2] != 0;
     if (n == 0 || overflow) { if (tid == 0) s.seg_kept[g] = 0; return; }
     const unsigned long long* m = mask + s.mask_off[g];
     unsigned long long* kb = keepbits + s.keep_off[g];
-    for (int w = tid; w < T; w += kSweepThreads) removed[w] = 0;
+    for (int w = tid; w < T; w += kSweepBigThreads) removed[w] = 0;
     int kept = 0;
     for (int b = 0; b < T; ++b) {
         const int nb = min(64, n - b * 64);
-        if (tid < nb) diag[tid] = m[(long long)(b * 64 + tid) * T + b];
+        if (tid < 64) diag[tid] = tid < nb ? m[(long long)(b * 64 + tid) * T + b] : 0ull;
+        __syncthreads();                               // diag ready; removed[] updates of the previous block visible
+        if (warp == 0) {
+            const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
+            unsigned long long R = removed[b] | invalid, C = 0;
+            const int t0 = lane, t1 = lane + 32;
+            const unsigned long long s0 = diag[t0] & ((1ull << t0) - 1ull);
+            const unsigned long long s1 = diag[t1] & ((1ull << t1) - 1ull);
+            while ((C | R) != ~0ull) {
+                const unsigned long long D = C | R;
+                bool c0 = false, r0 = false, c1 = false, r1 = false;
+                if (!((D >> t0) & 1ull)) { if (s0 & C) r0 = true; else if ((s0 & ~R) == 0ull) c0 = true; }
+                if (!((D >> t1) & 1ull)) { if (s1 & C) r1 = true; else if ((s1 & ~R) == 0ull) c1 = true; }
+                C |= (unsigned long long)__ballot_sync(0xffffffffu, c0) | ((unsigned long long)__ballot_sync(0xffffffffu, c1) << 32);
+                R |= (unsigned long long)__ballot_sync(0xffffffffu, r0) | ((unsigned long long)__ballot_sync(0xffffffffu, r1) << 32);
+            }
+            unsigned long long keepw = C;
+            if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
+                int extra = kept + __popcll(keepw) - max_keep;    // trim to exactly max_keep kept boxes in this segment
+                while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+            }
+            if (lane == 0) { s_keepw = keepw; kb[b] = keepw; }
+        }
         __syncthreads();
-        unsigned long long cur = removed[b];
-        unsigned long long keepw = 0;
-        if (nb == 64) {
-#pragma unroll 16
-            for (int t = 0; t < 64; ++t) {
-                const bool k = !((cur >> t) & 1ull);
-                keepw |= k ? (1ull << t) : 0ull;
-                cur |= k ? diag[t] : 0ull;
-            }
-        } else {
-            for (int t = 0; t < nb; ++t) {
-                const bool k = !((cur >> t) & 1ull);
-                keepw |= k ? (1ull << t) : 0ull;
-                cur |= k ? diag[t] : 0ull;
-            }
-        }
-        if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
-            // trim to exactly max_keep kept boxes in this segment
-            int extra = kept + __popcll(keepw) - max_keep;
-            while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
-        }
+        const unsigned long long keepw = s_keepw;
         kept += __popcll(keepw);
-        if (tid == 0) kb[b] = keepw;
-        const bool done = (max_keep > 0 && kept >= max_keep);
-        if (done) {
-            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
+        if (max_keep > 0 && kept >= max_keep) {
+            for (int w = b + 1 + tid; w < T; w += kSweepBigThreads) kb[w] = 0ull;
             break;
         }
-        for (int w = b + 1 + tid; w < T; w += kSweepThreads) {
-            unsigned long long acc = 0, bits = keepw;
-            while (bits) {
-                const int t0 = __ffsll((long long)bits) - 1; bits &= bits - 1;
-                unsigned long long v0 = m[(long long)(b * 64 + t0) * T + w], v1 = 0, v2 = 0, v3 = 0;
-                if (bits) { const int t1 = __ffsll((long long)bits) - 1; bits &= bits - 1; v1 = m[(long long)(b * 64 + t1) * T + w]; }
-                if (bits) { const int t2 = __ffsll((long long)bits) - 1; bits &= bits - 1; v2 = m[(long long)(b * 64 + t2) * T + w]; }
-                if (bits) { const int t3 = __ffsll((long long)bits) - 1; bits &= bits - 1; v3 = m[(long long)(b * 64 + t3) * T + w]; }
-                acc |= (v0 | v1) | (v2 | v3);
+        // kept row number r of this block (in bit order) goes to warp r % kWarps
+        unsigned long long bits = keepw;
+        for (int r = 0; bits; ++r) {
+            const int t = __ffsll((long long)bits) - 1; bits &= bits - 1;
+            if ((r % kWarps) != warp) continue;
+            const unsigned long long* row = m + (long long)(b * 64 + t) * T;
+            for (int c0 = b + 1 + lane; c0 < T; c0 += 32 * 8) {
+                unsigned long long v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { const int c = c0 + 32 * u; v[u] = c < T ? __ldg(row + c) : 0ull; }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) if (v[u]) atomicOr(&removed[c0 + 32 * u], v[u]);
             }
-            removed[w] |= acc;
         }
-        __syncthreads();
+        // the barrier at the top of the next iteration orders these updates before the next resolve
     }
     if (tid == 0) s.seg_kept[g] = kept;
 }
@@ -708,7 +717,7 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
         MB_CUDA(cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     }
-    k_nms_sweep<<<G, kSweepThreads, smem, stream>>>(s, mask, keepbits, max_keep);
+    k_nms_sweep<<<G, kSweepBigThreads, smem, stream>>>(s, mask, keepbits, max_keep);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

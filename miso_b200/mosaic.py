@@ -158,11 +158,12 @@ def infer_mosaic(model, mosaic_u8: Tensor, tile: int = 1024, overlap: int = 128,
     with torch.inference_mode():
         for i0 in range(0, len(mine), batch_size):
             idx = mine[i0:i0 + batch_size]
-            imgs = []
-            for t in idx:
-                y, x = grid[t]
-                imgs.append(mosaic_u8[y:y + tile, x:x + tile].permute(2, 0, 1).to(torch.float32) / 255)
-            res = model(imgs)
+            tiles = [mosaic_u8[grid[t][0]:grid[t][0] + tile, grid[t][1]:grid[t][1] + tile] for t in idx]
+            if getattr(model, "_miso_b200_patched", False) and mosaic_u8.dim() == 3 and mosaic_u8.shape[2] <= 4:
+                from .patch import forward_uint8
+                res = forward_uint8(model, tiles)        # ToTensor + normalize + resize + batch in one kernel
+            else:
+                res = model([t.permute(2, 0, 1).to(torch.float32) / 255 for t in tiles])
             for j, r in enumerate(res):
                 k = int(r["boxes"].shape[0])
                 boxes[i0 + j, :k], scores[i0 + j, :k], labels[i0 + j, :k] = r["boxes"], r["scores"], r["labels"]

@@ -12,8 +12,9 @@ from tests.test_mosaic_cpu import synth_tiles  # noqa: E402
 
 DEV = "cuda:0"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
-for world in (1, 2, 4, 8):
-    tiles, dpi = 4 * world, 300
+cases_ = [(w_, 4 * w_) for w_ in (1, 2, 4, 8)] + ([(0, 361)] if len(sys.argv) > 2 else [])
+for world, tiles in cases_:
+    dpi = 300
     b, s, l, c, o = synth_tiles(num_tiles=tiles, dpi=dpi, seed=1)
     c[:] = dpi
     block = mosaic.pack_block(*(torch.from_numpy(x).to(DEV) for x in (b, s, l)), torch.from_numpy(c).to(DEV).to(torch.int32),
@@ -28,4 +29,4 @@ for world in (1, 2, 4, 8):
         seam.launch(block, 0.5)
     e1.record(); torch.cuda.synchronize()
     kept = int(seam.nms.status[0])
-    print(f"world {world}: rows {block.shape[0]} kept {kept}  {e0.elapsed_time(e1) / reps:.4f} ms per seam NMS", flush=True)
+    print(f"world {world} tiles {tiles}: rows {block.shape[0]} kept {kept}  {e0.elapsed_time(e1) / reps:.4f} ms per seam NMS", flush=True)

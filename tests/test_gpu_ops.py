@@ -293,3 +293,24 @@ def test_transform_images(ops, golden_dir):
     rb, rs = D.transform_images(big, 800, 1333, mean, std)
     assert s2 == rs and tuple(b2.shape) == rb.shape == (3, 3, 800, 1152)
     assert np.array_equal(b2.cpu().numpy(), rb)
+
+
+@pytest.mark.parametrize("out_size", [(10, 6), (16, 16), (3, 3), (1, 1), (5, 14)])
+def test_roi_align_channels_last_other_output_sizes(ops, out_size):
+    """The 16-byte-gather kernel splits large outputs into bands of pooled rows (16x16 -> 6 + 6 + 4 rows) and
+    uses the plain copy-out when the staged chunk is not the output layout: still bit-exact."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((2, 24, 40, 52)).astype(np.float32)
+    rois = np.concatenate([rng.integers(0, 2, (60, 1)).astype(np.float32), cases.stress_rois(rng, 60, (160, 208), side=(4.0, 200.0))], 1)
+    xc = cu(x).contiguous(memory_format=torch.channels_last)
+    for aligned in (False, True):
+        out = ops.roi_align(xc, cu(rois), out_size, 0.25, 2, aligned).cpu().numpy()
+        assert np.array_equal(out, native.roi_align(x, rois, 0.25, out_size[0], out_size[1], 2, aligned))
+
+
+def test_transform_images_gray(ops):
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (90, 70, 1), dtype=np.uint8), rng.integers(0, 256, (64, 120, 1), dtype=np.uint8)]
+    b, s = ops.transform_images([cu(a) for a in imgs], 128, 200, [0.5], [0.25])
+    rb, rs = D.transform_images(imgs, 128, 200, [0.5], [0.25])
+    assert s == rs and np.array_equal(b.cpu().numpy(), rb)

@@ -57,7 +57,7 @@ static void carve_det(Carver& c, DetScratch& w, const DetDev& d) {
     w.P = P;
     w.img_max = c.take<float>(d.N);
     w.seg = carve_seg_arrays(c, G);       // seg_count must start at zero
-    w.zero_bytes = c.off;
+    w.zero_bytes = align_up(c.off, 16);   // (the next item starts 256-byte aligned: the round-up only covers padding)
     w.bkey = c.take<unsigned long long>(P);
     w.bbox = c.take<float4>(P);
     w.bseg = c.take<int>(P);
@@ -116,9 +116,14 @@ __global__ void __launch_bounds__(kDetThreads) k_det_candidates(const DetDev d, 
     if (vmax > 0.0f) atomicMax((int*)&w.img_max[n], __float_as_int(vmax));
 }
 
-__global__ void k_det_seg_starts(int G, int max_props, int* seg_start) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < G) seg_start[g] = g * max_props;
+// one launch for the per-call initialisation: clear the counters region, mark every bucket slot as a hole (-1)
+// and write the fixed segment starts (instead of two memsets and a kernel)
+__global__ void __launch_bounds__(256) k_det_init(int G, int max_props, int* __restrict__ seg_start, uint4* __restrict__ zero16,
+                                                  long long zero_vecs, int* __restrict__ bseg, long long P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+    for (long long j = i; j < zero_vecs; j += stride) zero16[j] = make_uint4(0u, 0u, 0u, 0u);
+    for (long long j = i; j < P; j += stride) bseg[j] = -1;
+    if (i < G) seg_start[i] = (int)i * max_props;
 }
 
 __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev d, const DetImages im, DetScratch w,
@@ -263,9 +268,9 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     carve_det(c, w, d);
     if (!c.ok()) return MB_ERR_WORKSPACE;
     const int G = d.N * (d.C - 1);
-    MB_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
-    MB_CUDA(cudaMemsetAsync(w.bseg, 0xff, sizeof(int) * w.P, stream));
-    k_det_seg_starts<<<ceil_div(G, 256), 256, 0, stream>>>(G, d.max_props, w.seg.seg_start);
+    if ((w.zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MB_ERR_INVALID_ARG;
+    k_det_init<<<max(ceil_div(G, 256), 32), 256, 0, stream>>>(G, d.max_props, w.seg.seg_start, (uint4*)workspace,
+                                                              (long long)(w.zero_bytes / 16), w.bseg, (long long)w.P);
     MB_LAUNCH_CHECK();
     k_det_candidates<<<ceil_div(d.N * d.max_props, kDetThreads), kDetThreads, 0, stream>>>(
         d, im, class_logits, box_regression, (const float4*)proposals, prop_counts, packed, w);

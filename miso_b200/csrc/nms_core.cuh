@@ -578,104 +578,6 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_wide(SegArra
     if (tid == 0) s.seg_kept[g] = kept;
 }
 
-// Same sweep with the segment's whole mask preloaded into shared memory by all threads at once
-// (one latency hit with maximal memory-level parallelism) — used when n * ceil(n/64) words fit.
-static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_preload(SegArrays s, const unsigned long long* __restrict__ mask,
-                                                                          unsigned long long* __restrict__ keepbits, int max_keep) {
-    extern __shared__ unsigned long long rowsm[];   // [n][T]
-    __shared__ unsigned long long removed[kSweepSmallMaxWords];
-    __shared__ unsigned long long s_keepw;
-    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = s.seg_count[g];
-    const int T = s.seg_words[g];
-    if (n == 0 || s.totals[2] != 0) { if (tid == 0) s.seg_kept[g] = 0; return; }
-    const unsigned long long* m = mask + s.mask_off[g];
-    unsigned long long* kb = keepbits + s.keep_off[g];
-    if (tid < T) removed[tid] = 0;
-    {   // rows are T words; only words >= the row's own block were written by the mask kernel.
-        // Thread = (column, row mod rows_per_pass) with the column count padded to a power of two (no
-        // division); 8 independent loads are issued before the first store (memory-level parallelism).
-        int lg = 0;
-        while ((1 << lg) < T) ++lg;
-        const int col = tid & ((1 << lg) - 1), r0 = tid >> lg, rstep = kSweepThreads >> lg;
-        if (col < T) {
-            for (int base = r0; base < n; base += 8 * rstep) {
-                unsigned long long v[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int row = base + u * rstep;
-                    v[u] = 0;
-                    if (row < n && col >= (row >> 6)) v[u] = __ldg(m + (size_t)row * T + col);
-                }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int row = base + u * rstep;
-                    if (row < n) rowsm[row * T + col] = v[u];
-                }
-            }
-        }
-    }
-    __syncthreads();
-    int kept = 0;
-    for (int b = 0; b < T; ++b) {
-        const int nb = min(64, n - b * 64);
-        const unsigned long long* tile = rowsm + (size_t)(b * 64) * T + b;   // word(t, col) = tile[t*T + col]
-        if (warp == 0) {
-            // Greedy resolve of the block. supp(t) = earlier boxes of the block that overlap box t (lower
-            // bits of its diagonal word); t is kept iff it is not removed from outside and no kept earlier
-            // box overlaps it. The loads do not depend on the chain, so the 64 steps cost ~4 dependent
-            // ALU operations each; every lane runs the same chain (no divergence, no exchange).
-            const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
-            const unsigned long long dead = removed[b] | invalid;
-            unsigned int klo = 0, khi = 0;
-#pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const unsigned int slo = (t < nb) ? (unsigned int)tile[t * T] : 0u;   // only earlier bits matter
-                const bool k = !((dead >> t) & 1ull) && ((slo & klo) == 0u);   // klo holds bits < t only
-                klo |= k ? (1u << t) : 0u;
-            }
-#pragma unroll
-            for (int t = 32; t < 64; ++t) {
-                const unsigned long long sw = (t < nb) ? tile[t * T] : 0ull;
-                const unsigned int slo = (unsigned int)sw, shi = (unsigned int)(sw >> 32);
-                const bool k = !((dead >> t) & 1ull) && (((slo & klo) | (shi & khi)) == 0u);   // khi holds bits < t only
-                khi |= k ? (1u << (t - 32)) : 0u;
-            }
-            unsigned long long keepw = ((unsigned long long)khi << 32) | klo;
-            if (max_keep > 0 && kept + __popcll(keepw) > max_keep) {
-                int extra = kept + __popcll(keepw) - max_keep;
-                while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
-            }
-            if (lane == 0) { s_keepw = keepw; kb[b] = keepw; }
-        }
-        __syncthreads();
-        const unsigned long long keepw = s_keepw;
-        kept += __popcll(keepw);
-        if (max_keep > 0 && kept >= max_keep) {
-            for (int w = b + 1 + tid; w < T; w += kSweepThreads) kb[w] = 0ull;
-            break;
-        }
-        {   // removed[b + col] |= OR of the kept rows' words: 4 adjacent lanes share a column (a quarter of the
-            // rows each), combine with two shuffles, and one of them owns the update (no atomics)
-            const int Wn = T - b;
-            const int col = 1 + (tid >> 2), q = tid & 3;
-            unsigned long long acc = 0;
-            if (col < Wn) {
-                unsigned long long bits = (keepw >> (16 * q)) & 0xffffull;
-                while (bits) {
-                    const int t = __ffsll((long long)bits) - 1 + 16 * q; bits &= bits - 1;
-                    acc |= tile[t * T + col];
-                }
-            }
-            acc |= __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc |= __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (q == 0 && col < Wn && acc) removed[b + col] |= acc;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) s.seg_kept[g] = kept;
-}
-
 inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsigned long long); }
 
 // Host helper: launch meta + mask + sweep on prepared sorted boxes.
@@ -685,16 +587,6 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     const float thr_up = strict_gt_threshold(iou_threshold);
     k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
-    const long long pre_bytes = (long long)max_seg_elems * ceil_div(max_seg_elems, 64) * 8;
-    // the whole-mask preload variant needs up to 160 KB of shared memory per CTA; measured slightly slower than the
-    // tile-at-a-time sweep and it cannot co-reside with RoIAlign CTAs of another stream, so it is opt-in (MB_SWEEP=p)
-    static const bool preload = [] { const char* e = getenv("MB_SWEEP"); return e && e[0] == 'p'; }();
-    if (preload && ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords && pre_bytes <= 160 * 1024) {
-        MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_preload, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pre_bytes));
-        k_nms_sweep_preload<<<G, kSweepThreads, (int)pre_bytes, stream>>>(s, mask, keepbits, max_keep);
-        MB_LAUNCH_CHECK();
-        return MB_OK;
-    }
     if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {   // (the wide kernel measured ~3 % slower at these sizes)
         k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);
         MB_LAUNCH_CHECK();

@@ -1013,8 +1013,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         if (!(p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)))
             return MB_ERR_UNSUPPORTED;   // the host converts to NCHW for other configurations
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
-        const char* nv = getenv("MB_ROI_NHWC");
-        const bool vec = (nv == nullptr || strcmp(nv, "scalar") != 0) && (p.channels % 4 == 0);
+        const bool vec = p.channels % 4 == 0;
         bool aligned16 = true;
         for (int l = 0; l < p.num_levels; ++l) aligned16 = aligned16 && ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) == 0);
         bool small_maps = true;   // 32-bit byte offsets inside one image
@@ -1051,8 +1050,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
     }
     if (staged && p.sampling_ratio == 2 && nbins <= 256 && p.pooled_h <= 16 && p.pooled_w <= 16 && num_rois < (1ll << 31)) {
         const int opitch = (nbins & 1) ? nbins : nbins + 1;
-        const char* vs = getenv("MB_ROI_VARIANT");
-        const int variant = vs != nullptr ? atoi(vs) : 2;   // bit0: no float4 staging, bit1: 16 scalar loads in flight
+        const int variant = 2;   // bit0: no float4 staging, bit1: 16 scalar loads in flight (measured best: 2)
         const int patch_floats = kChunk * 321;   // footprint of up to 321 pixels per channel: 4 CTAs/SM at 7x7
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;

@@ -518,14 +518,27 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_wide(SegArra
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    stage(0, tiles);
+    // ring of nbuf tile buffers: tiles b+1 .. b+nbuf-1 are in flight while block b is resolved, so the global-load
+    // latency of a tile (the dominant cost of a block step) is spread over nbuf-1 steps
+    const size_t tile_words = (size_t)64 * Tcap;
+    for (int q = 0; q < nbuf - 1; ++q) {
+        if (q < T) stage(q, tiles + q * tile_words);
+        else asm volatile("cp.async.commit_group;" ::: "memory");     // keep one group per step for the wait arithmetic
+    }
+    if (nbuf == 1) stage(0, tiles);
     int kept = 0;
     for (int b = 0; b < T; ++b) {
         const int nb = min(64, n - b * 64), Wn = T - b;
-        unsigned long long* tile = tiles + (size_t)(nbuf > 1 ? (b & 1) : 0) * 64 * Tcap;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();                                   // tile b complete and visible; buffer (b+1)&1 is free
-        if (nbuf > 1 && b + 1 < T) stage(b + 1, tiles + (size_t)((b + 1) & 1) * 64 * Tcap);
+        unsigned long long* tile = tiles + (size_t)(b % nbuf) * tile_words;
+        // groups committed so far: tiles 0 .. b+nbuf-2 (one per step); tile b is complete when at most nbuf-2 are pending
+        if (nbuf >= 4) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (nbuf == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();                                   // tile b complete and visible; buffer (b-1) % nbuf is free
+        if (nbuf > 1) {
+            if (b + nbuf - 1 < T) stage(b + nbuf - 1, tiles + (size_t)((b + nbuf - 1) % nbuf) * tile_words);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (warp == 0) {
             const unsigned long long invalid = nb < 64 ? ~((1ull << nb) - 1ull) : 0ull;
             unsigned long long R = removed[b] | invalid, C = 0;
@@ -573,7 +586,7 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_wide(SegArra
             __syncthreads();                               // everyone is done with the tile before it is overwritten
             if (b + 1 < T) stage(b + 1, tiles);
         }
-        // nbuf == 2: the barrier at the top of the next iteration orders this OR phase before block b+1's resolve
+        // nbuf > 1: the barrier at the top of the next iteration orders this OR phase before block b+1's resolve
     }
     if (tid == 0) s.seg_kept[g] = kept;
 }
@@ -587,16 +600,17 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     const float thr_up = strict_gt_threshold(iou_threshold);
     k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
     MB_LAUNCH_CHECK();
-    if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {   // (the wide kernel measured ~3 % slower at these sizes)
+    // (the cp.async ring kernel below measured 8-12 % slower than this one at <= 4096 boxes, at every ring depth)
+    if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {
         k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);
         MB_LAUNCH_CHECK();
         return MB_OK;
     }
-    {   // wide tiled sweep: removed[] + one or two 64-row tiles in dynamic shared memory
+    {   // tiled sweep with a ring of cp.async tile buffers in dynamic shared memory: removed[] + nbuf 64-row tiles
         const int Tcap = ceil_div(max_seg_elems, 64);
-        const long long one = ((long long)Tcap + 64ll * Tcap) * 8, two = ((long long)Tcap + 128ll * Tcap) * 8;
-        const int nbuf = two <= 200 * 1024 ? 2 : 1;
-        const long long bytes = nbuf == 2 ? two : one;
+        int nbuf = 4;
+        while (nbuf > 1 && ((long long)Tcap + 64ll * nbuf * Tcap) * 8 > 200 * 1024) --nbuf;
+        const long long bytes = ((long long)Tcap + 64ll * nbuf * Tcap) * 8;
         if (bytes <= 200 * 1024) {
             MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
             k_nms_sweep_wide<<<G, kSweepThreads, (int)bytes, stream>>>(s, mask, keepbits, max_keep, Tcap, nbuf);

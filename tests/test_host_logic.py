@@ -41,3 +41,18 @@ def test_infer_scale_and_base_anchors():
     ag = AnchorGenerator(((32,), (64,)), ((0.5, 1.0, 2.0), (0.5, 1.0, 2.0)))
     for i, s in enumerate((32, 64)):
         assert torch.equal(ops.base_anchors((s,), (0.5, 1.0, 2.0)), ag.cell_anchors[i])
+
+
+def test_resized_image_size_matches_torchvision_transform():
+    """ops.resized_image_size (host arithmetic of the fused input transform) against the sizes torchvision's
+    GeneralizedRCNNTransform produces on the CPU, for shapes on both sides of the min/max rule."""
+    import torch
+    from torchvision.models.detection.transform import GeneralizedRCNNTransform
+    from miso_b200 import ops
+    rng = np.random.default_rng(0)
+    for mn, mx in ((800, 1333), (96, 150), (224, 224)):
+        tr = GeneralizedRCNNTransform(mn, mx, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0]).eval()
+        for _ in range(12):
+            h, w = int(rng.integers(17, 400)), int(rng.integers(17, 400))
+            il, _ = tr([torch.zeros(3, h, w)])
+            assert tuple(il.image_sizes[0]) == ops.resized_image_size(h, w, mn, mx), (h, w, mn, mx)

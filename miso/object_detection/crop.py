@@ -1,8 +1,11 @@
 """crop_objects (ref:miso/object_detection/crop.py:9-33): same output tree and file names; the
-pixel gather for all boxes of an image is one mb_crop_plan + mb_crop_gather on the device."""
+pixel gather for all boxes of an image is one mb_crop_plan + mb_crop_gather on the device, one
+device-to-host copy hands over all crops of the image, and the files are encoded and written by a
+thread pool (the reference encodes them one by one with skimage.io.imsave)."""
 from __future__ import annotations
 
 import os
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 import numpy as np
@@ -16,6 +19,12 @@ def crop_objects(project: Project, output_dir: str, relative_to=None):
     from miso_b200 import detection
     os.makedirs(output_dir, exist_ok=True)
     output_path = Path(output_dir)
+    pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    pending = []
+
+    def save(arr, target):
+        Image.fromarray(arr).save(target)
+
     for image in project.image_dict.values():
         if len(image.boxes) == 0:
             continue
@@ -39,4 +48,7 @@ def crop_objects(project: Project, output_dir: str, relative_to=None):
             s = box.bounds
             filename = f"{path.stem}_{s[0]:.0f}_{s[1]:.0f}_{s[2]:.0f}_{s[3]:.0f}{path.suffix}"
             if crop.size:
-                Image.fromarray(crop).save(os.path.join(str(label_path), filename))
+                pending.append(pool.submit(save, crop, os.path.join(str(label_path), filename)))
+    for f in pending:
+        f.result()                      # re-raise encoder / file-system errors
+    pool.shutdown()

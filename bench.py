@@ -255,7 +255,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from miso_b200 import mosaic, pipeline, workload
-    from miso_b200 import ops as mops
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

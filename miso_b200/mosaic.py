@@ -16,7 +16,7 @@ The only collective is one all_gather_into_tensor of [tiles_per_rank_max * dpi, 
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -55,7 +55,6 @@ def pack_block(det_boxes: Tensor, det_scores: Tensor, det_labels: Tensor, det_co
     the host logic): the same arithmetic with tensor operations."""
     t, dpi = det_scores.shape
     if det_boxes.is_cuda:
-        import ctypes as C
         from . import _lib
         from .ops import _ptr, _stream
         if out is None:

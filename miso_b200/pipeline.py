@@ -9,13 +9,16 @@ One `step()` is what happens between the CNN heads and the saved particle crops 
     detections + original uint8 images ──► mb_crop_plan / mb_crop_gather ──► packed crops
 
 All parameter structs, workspaces and outputs are created once; `step()` only enqueues kernels
-on the current stream (6 C-ABI calls, no allocation, no host synchronisation).
+on the current stream (6 C-ABI calls, no allocation, no host synchronisation). `OverlappedHotPath`
+keeps three batches in flight on three streams, `HostPipeline` is the pinned-host-in / pinned-host-out
+loop around it, `HotPath.capture()` records the step as a CUDA graph.
 """
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -24,7 +27,6 @@ from . import _lib
 from ._lib import CropParams, DetParams, MisoB200Error, RoiAlignParams, RpnParams
 from .detection import DetConfig, RpnConfig
 from .ops import _ptr, base_anchors, infer_scale, level_thresholds
-import math
 
 
 @dataclass

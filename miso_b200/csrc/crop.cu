@@ -52,36 +52,45 @@ __global__ void __launch_bounds__(1024) k_crop_plan(const CropDev d, const float
     if (tid == 0) { s_cnt = 0; s_bytes = 0; }
     __syncthreads();
     const int total = d.N * d.cap;
-    for (int e0 = 0; e0 < total; e0 += 1024) {
-        const int e = e0 + tid;
-        bool ok = false;
-        int4 rc = make_int4(0, 0, 0, 0);
-        float4 an = make_float4(0, 0, 0, 0);
-        long long nbytes = 0;
-        if (e < total) {
-            const int n = e / d.cap, i = e - n * d.cap;
-            if (i < counts[n] && scores[e] > d.thr) {
-                ok = true;
-                const float4 b = boxes[e];
-                an = d.xywh ? b : make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-                const long long c0 = round_half_even_to_int(an.x), c1 = round_half_even_to_int(an.y);
-                const long long c2 = round_half_even_to_int(__fadd_rn(an.x, an.z));
-                const long long c3 = round_half_even_to_int(__fadd_rn(an.y, an.w));
-                resolve_slice(c0, c2, d.w[n], rc.x, rc.z);
-                resolve_slice(c1, c3, d.h[n], rc.y, rc.w);
-                nbytes = (long long)rc.z * rc.w * d.ch;
+    constexpr int kE = 4;                             // consecutive entries per thread: 4096 per round, one round for the usual N * cap
+    for (int e0 = 0; e0 < total; e0 += 1024 * kE) {
+        bool ok[kE];
+        int4 rc[kE];
+        float4 an[kE];
+        long long nbytes[kE];
+        int cnt = 0;
+        long long bytes = 0;
+#pragma unroll
+        for (int k = 0; k < kE; ++k) {
+            const int e = e0 + tid * kE + k;
+            ok[k] = false; rc[k] = make_int4(0, 0, 0, 0); an[k] = make_float4(0, 0, 0, 0); nbytes[k] = 0;
+            if (e < total) {
+                const int n = e / d.cap, i = e - n * d.cap;
+                if (i < counts[n] && scores[e] > d.thr) {
+                    ok[k] = true;
+                    const float4 b = boxes[e];
+                    an[k] = d.xywh ? b : make_float4(b.x, b.y, __fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+                    const long long c0 = round_half_even_to_int(an[k].x), c1 = round_half_even_to_int(an[k].y);
+                    const long long c2 = round_half_even_to_int(__fadd_rn(an[k].x, an[k].z));
+                    const long long c3 = round_half_even_to_int(__fadd_rn(an[k].y, an[k].w));
+                    resolve_slice(c0, c2, d.w[n], rc[k].x, rc[k].z);
+                    resolve_slice(c1, c3, d.h[n], rc[k].y, rc[k].w);
+                    nbytes[k] = (long long)rc[k].z * rc[k].w * d.ch;
+                    ++cnt; bytes += nbytes[k];
+                }
             }
         }
-        // stable compaction: exclusive scan of (flag, bytes) over the 1024 entries of this round
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        long long bs = nbytes;
+        // stable compaction: exclusive scan of (count, bytes) over the threads of this round (entries of a thread
+        // are consecutive, threads are in entry order)
+        int cs = cnt;
+        long long bs = bytes;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, bs, o);
-            if (lane >= o) bs += y;
+            const int yc = __shfl_up_sync(0xffffffffu, cs, o);
+            const long long yb = __shfl_up_sync(0xffffffffu, bs, o);
+            if (lane >= o) { cs += yc; bs += yb; }
         }
-        if (lane == 31) wbytes[wid] = bs;
-        if (lane == 0) wcnt[wid] = __popc(m);
+        if (lane == 31) { wcnt[wid] = cs; wbytes[wid] = bs; }
         __syncthreads();
         int pc = 0, tc = 0;
         long long pb = 0, tb = 0;
@@ -91,12 +100,17 @@ __global__ void __launch_bounds__(1024) k_crop_plan(const CropDev d, const float
         }
         const int base_c = s_cnt;
         const long long base_b = s_bytes;
-        if (ok) {
-            const int j = base_c + pc + __popc(m & ((1u << lane) - 1));
-            rects[j] = rc;
-            xywh[j] = an;
-            src[j] = e;
-            offsets[j] = base_b + pb + bs - nbytes;
+        int j = base_c + pc + cs - cnt;
+        long long off = base_b + pb + bs - bytes;
+#pragma unroll
+        for (int k = 0; k < kE; ++k) {
+            if (ok[k]) {
+                rects[j] = rc[k];
+                xywh[j] = an[k];
+                src[j] = e0 + tid * kE + k;
+                offsets[j] = off;
+                ++j; off += nbytes[k];
+            }
         }
         __syncthreads();
         if (tid == 0) { s_cnt = base_c + tc; s_bytes = base_b + tb; }

@@ -224,3 +224,27 @@ def test_seam_nms_sync_free_equals_compacting_version(det):
     seam.launch(block, 0.5)
     gb2, _, _ = seam.finish()
     assert torch.equal(gb2, gb)
+
+
+def test_filter_and_crop_many_slots_multi_round(det):
+    """24 images x 200 slots = 4800 detection slots: more than one 4096-entry round of the plan kernel;
+    every image's crops must equal the oracle's, in order, with ragged counts and scores on both sides of
+    the threshold."""
+    rng = np.random.default_rng(17)
+    n, cap, hw = 24, 200, (96, 128)
+    imgs = [rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8) for _ in range(n)]
+    db = np.zeros((n, cap, 4), np.float32); ds = np.zeros((n, cap), np.float32)
+    cnt = rng.integers(0, cap + 1, n).astype(np.int32)
+    for i in range(n):
+        db[i] = cases.stress_rois(rng, cap, hw, side=(2.0, 90.0))
+        ds[i] = rng.uniform(0.0, 1.0, cap).astype(np.float32)
+    out = det.filter_and_crop([cu(a) for a in imgs], cu(db), cu(ds), cu(cnt), 0.5)
+    crops = out.to_host(3)
+    k = 0
+    for i in range(n):
+        _, _, _, rxywh, _, rcrops = M.filter_and_crop(imgs[i], db[i, :cnt[i]], ds[i, :cnt[i]], np.ones(cnt[i], np.int64), 0.5)
+        for xy, ref in zip(rxywh, rcrops):
+            img_idx, _, gxy, arr = crops[k]
+            assert img_idx == i and np.array_equal(gxy, xy) and arr.shape == ref.shape and np.array_equal(arr, ref)
+            k += 1
+    assert k == len(crops) and k > 1000

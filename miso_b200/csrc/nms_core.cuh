@@ -103,6 +103,37 @@ static __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, in
     __shared__ long long sh[64];
     __shared__ long long carry[4];
     const int tid = threadIdx.x;
+    if (G <= 32) {
+        // the hot-path case (image x level or image x class segments): one warp, shuffle scans, no barriers
+        if (tid < 32) {
+            const int n = tid < G ? s.seg_count[tid] : 0;
+            const long long T = (n + 63) >> 6;
+            long long v[4] = {(long long)n, (long long)n * T, T * (T + 1) / 2, T}, inc[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                inc[q] = v[q];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long y = __shfl_up_sync(0xffffffffu, inc[q], o);
+                    if (tid >= o) inc[q] += y;
+                }
+            }
+            if (tid < G) {
+                if (compute_starts) s.seg_start[tid] = (int)(inc[0] - v[0]);
+                s.seg_words[tid] = (int)T;
+                s.mask_off[tid] = inc[1] - v[1];
+                s.tile_pre[tid] = inc[2] - v[2];
+                s.keep_off[tid] = (int)(inc[3] - v[3]);
+            }
+            if (tid == 31) {
+                s.tile_pre[G] = inc[2];
+                s.keep_off[G] = (int)inc[3];
+                s.totals[0] = inc[2];
+                s.totals[1] = inc[1];
+                s.totals[2] = inc[1] > mask_cap_words ? 1 : 0;
+            }
+        }
+    } else {
     if (tid < 4) carry[tid] = 0;
     __syncthreads();
     for (int base = 0; base < G; base += 1024) {
@@ -141,6 +172,7 @@ static __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, in
         s.totals[0] = carry[2];
         s.totals[1] = carry[1];
         s.totals[2] = carry[1] > mask_cap_words ? 1 : 0;
+    }
     }
     if (rule.segs_per_image > 0) {
         for (int g = tid; g < G; g += 1024) {

@@ -135,13 +135,16 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_hist(const RpnDev d, RpnScr
     __threadfence();
     __shared__ long long scan_sh[64];
     const int k = d.k[l];
-    int carry = 0;
-    for (int base = 0; base < kHistBins; base += kRpnThreads) {
-        const int v = __ldcg(&gh[base + tid]);
-        long long tot;
-        const int pre = carry + (int)block_excl_scan_1024(v, scan_sh, tot);
-        if (pre < k && pre + v >= k) { w.thr_bin[g] = base + tid; w.n_above[g] = pre; }
-        carry += (int)tot;
+    static_assert(kHistBins == 4 * kRpnThreads, "one thread per four consecutive bins");
+    int v[4], sum = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = __ldcg(&gh[4 * tid + q]); sum += v[q]; }
+    long long tot;
+    int acc = (int)block_excl_scan_1024(sum, scan_sh, tot);       // one block scan over the per-thread sums
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (acc < k && acc + v[q] >= k) { w.thr_bin[g] = 4 * tid + q; w.n_above[g] = acc; }
+        acc += v[q];
     }
 }
 
@@ -337,17 +340,18 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
         run_off[d.L] = acc;
     }
     __syncthreads();
-    for (int l = 0; l < d.L; ++l) {
-        const int g = n * d.L + l;
-        const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
-        const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
-        for (int q = tid; q < cnt; q += kRpnThreads) {
-            const unsigned long long word = kb[q >> 6];
-            if ((word >> (q & 63)) & 1ull) {
-                const int j = wpre[l][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull));
-                const int p = st + q;
-                keys[run_off[l] + j] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
-            }
+    // one flat loop over the candidate slots of all levels (slot e of the image belongs to level l with
+    // koff[l] <= e < koff[l+1]): the dependent global loads of different levels overlap
+    for (int e = tid; e < Ktot; e += kRpnThreads) {
+        int l = 0;
+        while (l + 1 < d.L && e >= d.koff[l + 1]) ++l;
+        const int g = n * d.L + l, q = e - d.koff[l];
+        if (q >= w.seg.seg_count[g]) continue;
+        const unsigned long long word = w.keepbits[w.seg.keep_off[g] + (q >> 6)];
+        if ((word >> (q & 63)) & 1ull) {
+            const int j = wpre[l][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull));
+            const int p = w.seg.seg_start[g] + q;
+            keys[run_off[l] + j] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
         }
     }
     __syncthreads();

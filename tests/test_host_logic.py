@@ -56,3 +56,22 @@ def test_resized_image_size_matches_torchvision_transform():
             h, w = int(rng.integers(17, 400)), int(rng.integers(17, 400))
             il, _ = tr([torch.zeros(3, h, w)])
             assert tuple(il.image_sizes[0]) == ops.resized_image_size(h, w, mn, mx), (h, w, mn, mx)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs first) needs no GPU and no CUDA library: one JSON
+    line with the contract's keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "detections_per_sec_posthead_path" and line["value"] > 0
+    for key in ("unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+                "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["cpu_baseline"]["kind"] == "reference" and line["e2e"]["h2d_bytes_per_step"] == 0

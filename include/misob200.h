@@ -99,6 +99,9 @@ typedef struct {
      * torch.channels_last cuDNN backbone produces). The kernel then gathers 128-byte channel
      * vectors straight from global memory / L1 and needs no shared-memory staging. */
     int32_t channels_last;
+    /* != 0: skip the TMA-staged kernel and take the register-gather kernel (k_roi_align_nhwc4d); for A/B
+     * measurements and tests — both produce identical results. */
+    int32_t force_gather;
 } mb_roi_align_params;
 /* Optional workspace: when non-zero and provided, NCHW maps are transposed once to channels-last and
  * gathered from there (faster when the RoIs' footprints cover the pyramid several times over). */

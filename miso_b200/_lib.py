@@ -32,7 +32,7 @@ class RoiAlignParams(C.Structure):
         ("height", _i32 * MB_MAX_LEVELS), ("width", _i32 * MB_MAX_LEVELS),
         ("spatial_scale", _f32 * MB_MAX_LEVELS), ("level_thresholds", _f32 * MB_MAX_LEVELS),
         ("features", _p * MB_MAX_LEVELS),
-        ("boxes_per_image", _i32), ("box_counts", _p), ("channels_last", _i32),
+        ("boxes_per_image", _i32), ("box_counts", _p), ("channels_last", _i32), ("force_gather", _i32),
     ]
 
 

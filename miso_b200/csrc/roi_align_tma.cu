@@ -1,0 +1,562 @@
+// roi_align_tma.cu — MultiScaleRoIAlign forward for channels-last fp32 maps: a persistent, warp-specialised
+// kernel that stages every RoI's footprint through TMA bulk copies into a shared-memory ring.
+//
+// Replaces tv:ops/poolers.py:147-227 + torchvision::roi_align (tv-csrc:ops/cpu/roi_align_kernel.cpp:393,
+// SURVEY.md Appendix B.2) on the fast route of mb_multiscale_roi_align (sampling_ratio 2, aligned=False).
+//
+// Why: the gather kernel (k_roi_align_nhwc4d) was latency-bound — each warp had 9 LDG.128 in flight and waited
+// for them (profiles/r1_roi_align_nhwc4d_ncu_full.txt: 35 % resident warps, 42 % of stalls on the first use
+// after the loads) — and pulled every pixel 2.3x through L1 because neighbouring bins share taps. Here
+//   * one CTA per SM (grid = #SMs), RoIs round-robin; 16 warps: 14 consumers, 1 producer, 1 store warp;
+//   * the producer warp builds the RoI's tap tables (lanes = samples) one RoI ahead and streams the touched
+//     pixel rows of the footprint — in channels-last memory a footprint row is ONE contiguous run of
+//     FW*C*4 bytes — with cp.async.bulk (TMA) into a byte ring in shared memory, each row on its own
+//     mbarrier; no registers are held per byte in flight and the copies run ahead across RoI boundaries;
+//   * consumer warps walk the pooled rows in order; task = (bin, 128 channels), lane = 4 consecutive channels:
+//     the distinct taps of the bin (3x3 typically) are LDS.128 from the ring, the 16 weight x value products
+//     keep the reference order (exact mode: packed FMUL2 + FFMA2 with an opaque multiplier 1.0f, which is an
+//     exactly rounded add that ptxas cannot contract with the multiply) or use FMAs;
+//     rows are released (per-row "empty" mbarrier) as soon as no later pooled row needs them;
+//   * the RoI's outputs are collected in shared memory in the output layout [C][PH*PW] (double buffered) and
+//     leave as one bulk async copy issued by the store warp.
+// Every pixel row crosses L2->SM once per RoI, and the loads are decoupled from the arithmetic.
+#include "common.cuh"
+#include "roi_common.cuh"
+
+namespace mb {
+
+constexpr int kTmaConsumers = 14;
+constexpr int kTmaThreads = (kTmaConsumers + 2) * 32;
+constexpr int kRowSlots = 64;     // row descriptors / barriers in flight
+constexpr int kMaxPool = 16;
+
+struct __align__(16) TmaGeom {
+    int mode;                // 0: zeros, 1: rows staged by TMA, 2: direct global gathers (rows wider than the ring allows)
+    int seq0;                // sequence number of the RoI's first staged row
+    int nrows;               // staged rows
+    int pad;
+    unsigned long long img;  // mode 2: address of the image's map at this level
+    unsigned long long pad2;
+    int4 yidx[kMaxPool];     // 4 row slots of a pooled row: ordinals of the staged rows (mode 1) / byte offsets y*W*C*4 (mode 2)
+    float4 ywa[kMaxPool];    // (h0, h0, l0, l0)
+    float4 ywb[kMaxPool];    // (h1, h1, l1, l1)
+    uint4 xoff[kMaxPool];    // 4 column slots of a pooled column: byte offsets inside the staged row / the map row
+    float4 xwa[kMaxPool];
+    float4 xwb[kMaxPool];
+    int yinfo[kMaxPool];     // pattern (0..2) | valid bits << 2 | rows that must have landed << 8 | rows releasable afterwards << 16
+    int xinfo[kMaxPool];     // pattern | valid bits << 2
+};
+
+// ---- mbarrier / bulk-copy primitives (PTX) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A wait that cannot hang the GPU: a barrier that never completes (a protocol bug) traps after ~seconds.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;" ::"l"(dst),
+                 "r"(src), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+          "l"(reinterpret_cast<unsigned long long&>(c)));
+    return reinterpret_cast<float2&>(d);
+}
+
+// one tap of 4 consecutive channels; RowT = unsigned (shared-memory address) or const char* (global)
+__device__ __forceinline__ float4 tap_ld(unsigned row, unsigned off) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(row + off));
+    return v;
+}
+__device__ __forceinline__ float4 tap_ld(const char* row, unsigned off) {
+    return __ldg(reinterpret_cast<const float4*>(row + off));
+}
+
+// the reference's per-sample sum for two channels: acc + (((w1*v1 + w2*v2) + w3*v3) + w4*v4)
+template <bool EXACT>
+__device__ __forceinline__ float2 sample2(float2 w1, float2 w2, float2 w3, float2 w4, float2 v1, float2 v2, float2 v3,
+                                          float2 v4, float2 acc, float2 ones) {
+    if (EXACT) {
+        // fma(p, 1.0f, t) == fl(p + t): every product and every sum is rounded once, like the CPU kernel. `ones`
+        // comes from the kernel parameters, so ptxas can neither fold it nor contract the multiply into the add.
+        float2 t = mul2_rn(w1, v1);
+        t = fma2_rn(mul2_rn(w2, v2), ones, t);
+        t = fma2_rn(mul2_rn(w3, v3), ones, t);
+        t = fma2_rn(mul2_rn(w4, v4), ones, t);
+        return fma2_rn(t, ones, acc);
+    } else {
+        return fma2_rn(w1, v1, fma2_rn(w2, v2, fma2_rn(w3, v3, fma2_rn(w4, v4, acc))));
+    }
+}
+
+// All four samples valid: the 16 taps are the product of the bin's distinct rows and columns (patterns of
+// axis_pattern: 0 = both samples in one cell, 1 = they share a pixel, 2 = four pixels); each distinct pixel is loaded once.
+template <bool EXACT, int PY, int PX, typename RowT>
+__device__ __forceinline__ float4 bin_fast(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&wy)[4],
+                                           const float2 (&wx)[4], float2 ones) {
+    constexpr int NR = PY == 0 ? 2 : (PY == 1 ? 3 : 4), NC = PX == 0 ? 2 : (PX == 1 ? 3 : 4);
+    float4 G[NR][NC];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) G[r][c] = tap_ld(rb[r], co[c]);
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int iy = smp >> 1, ix = smp & 1;
+        const int yl = iy == 0 ? 0 : (PY == 0 ? 0 : (PY == 1 ? 1 : 2)), yh = iy == 0 ? 1 : (PY == 0 ? 1 : (PY == 1 ? 2 : 3));
+        const int xl = ix == 0 ? 0 : (PX == 0 ? 0 : (PX == 1 ? 1 : 2)), xh = ix == 0 ? 1 : (PX == 0 ? 1 : (PX == 1 ? 2 : 3));
+        const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
+        const float2 w1 = mul2_rn(hyv, hxv), w2 = mul2_rn(hyv, lxv), w3 = mul2_rn(lyv, hxv), w4 = mul2_rn(lyv, lxv);
+        const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
+        lo = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y),
+                            make_float2(v4.x, v4.y), lo, ones);
+        hi = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w),
+                            make_float2(v4.z, v4.w), hi, ones);
+    }
+    const float2 q = make_float2(0.25f, 0.25f);     // acc / 4 samples: exact scaling
+    lo = mul2_rn(lo, q);
+    hi = mul2_rn(hi, q);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// Any sample may be invalid (skipped like the reference does — no zero-weight multiply, so a NaN/Inf feature
+// never leaks into a bin it does not belong to); slots are the raw (A.lo, A.hi, B.lo, B.hi) of each axis.
+template <bool EXACT, typename RowT>
+__device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&wy)[4],
+                                              const float2 (&wx)[4], int yvalid, int xvalid, float2 ones) {
+    float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int iy = smp >> 1, ix = smp & 1;
+        if (!((yvalid >> iy) & 1) || !((xvalid >> ix) & 1)) continue;       // warp-uniform
+        const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
+        const float2 w1 = mul2_rn(hyv, hxv), w2 = mul2_rn(hyv, lxv), w3 = mul2_rn(lyv, hxv), w4 = mul2_rn(lyv, lxv);
+        const float4 v1 = tap_ld(rb[2 * iy], co[2 * ix]), v2 = tap_ld(rb[2 * iy], co[2 * ix + 1]);
+        const float4 v3 = tap_ld(rb[2 * iy + 1], co[2 * ix]), v4 = tap_ld(rb[2 * iy + 1], co[2 * ix + 1]);
+        lo = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y),
+                            make_float2(v4.x, v4.y), lo, ones);
+        hi = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w),
+                            make_float2(v4.z, v4.w), hi, ones);
+    }
+    const float2 q = make_float2(0.25f, 0.25f);
+    lo = mul2_rn(lo, q);
+    hi = mul2_rn(hi, q);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+struct TmaSmem {          // carve-up of the dynamic shared memory (offsets in bytes)
+    unsigned ring, ob, geom, rowoff, rowy, bars, total;
+};
+__host__ __device__ inline TmaSmem tma_smem_layout(unsigned ring_bytes, unsigned ob_bytes) {
+    TmaSmem s;
+    s.ring = 0;
+    s.ob = ring_bytes;
+    s.geom = s.ob + 2 * ob_bytes;
+    s.rowoff = s.geom + 2 * (unsigned)sizeof(TmaGeom);
+    s.rowy = s.rowoff + kRowSlots * 4;
+    s.bars = s.rowy + kRowSlots * 4;
+    s.total = s.bars + (2 * kRowSlots + 8) * 8;
+    return s;
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __restrict__ rois, int num_rois,
+                float* __restrict__ out, int* __restrict__ levels_out, unsigned ring_bytes, unsigned row_cap, float2 ones) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW, C = p.channels;
+    const unsigned ob_bytes = (unsigned)C * nbins * 4u;
+    const TmaSmem L = tma_smem_layout(ring_bytes, ob_bytes);
+    TmaGeom* geom = reinterpret_cast<TmaGeom*>(smem_raw + L.geom);
+    volatile int* rowoff = reinterpret_cast<volatile int*>(smem_raw + L.rowoff);
+    int* rowy = reinterpret_cast<int*>(smem_raw + L.rowy);
+    const unsigned s_base = smem_u32(smem_raw);
+    const unsigned b_full = s_base + L.bars, b_empty = b_full + kRowSlots * 8, b_gfull = b_empty + kRowSlots * 8;
+    const unsigned b_gempty = b_gfull + 16, b_ofull = b_gempty + 16, b_ofree = b_ofull + 16;
+
+    if (tid == 0) {
+        for (int i = 0; i < kRowSlots; ++i) {
+            mbar_init(b_full + 8 * i, 1);
+            mbar_init(b_empty + 8 * i, kTmaConsumers);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(b_gfull + 8 * i, 1);
+            mbar_init(b_gempty + 8 * i, kTmaConsumers);
+            mbar_init(b_ofull + 8 * i, kTmaConsumers);
+            mbar_init(b_ofree + 8 * i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    if (warp == kTmaConsumers) {
+        // =========================== producer: tap tables + TMA row copies ===========================
+        int next_seq = 0, tail_seq = 0;
+        unsigned head = 0;
+        int it = 0;
+        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
+            const int par = it & 1;
+            if (it >= 2) mbar_wait(b_gempty + 8 * par, ((it >> 1) - 1) & 1);
+            TmaGeom& G = geom[par];
+            float r[5];
+            load_roi(rois, k, p, r);
+            RoiGeom g;
+            roi_geometry(r, p, g);
+            if (levels_out != nullptr && lane == 0) levels_out[k] = g.level;
+            const bool dead = g.batch < 0 || g.batch >= p.num_images;
+            // ---- x axis ----
+            Tap tx = make_tap(g.start_w, g.bin_w, lane >> 1, lane & 1, 2, g.W);
+            if (lane >= 2 * PW) tx.valid = 0;
+            const unsigned xm = __ballot_sync(full, tx.valid != 0);
+            Tap ty = make_tap(g.start_h, g.bin_h, lane >> 1, lane & 1, 2, g.H);
+            if (lane >= 2 * PH) ty.valid = 0;
+            const unsigned ym = __ballot_sync(full, ty.valid != 0);
+            int mode = (dead || xm == 0 || ym == 0) ? 0 : 1;
+            int x0 = 0, fw = 0, nrows = 0;
+            if (mode != 0) {
+                const int fx = __ffs(xm) - 1, lx = 31 - __clz(xm), fy = __ffs(ym) - 1, ly = 31 - __clz(ym);
+                x0 = __shfl_sync(full, tx.lo, fx);
+                fw = __shfl_sync(full, tx.hi, lx) - x0 + 1;
+                // valid samples must be one run with non-decreasing pixel indices (bin size > 0 guarantees it);
+                // anything else takes the direct route, which does not rely on it
+                const int plo_x = __shfl_up_sync(full, tx.lo, 1), plo_y = __shfl_up_sync(full, ty.lo, 1);
+                const int phi_x = __shfl_up_sync(full, tx.hi, 1), phi_y = __shfl_up_sync(full, ty.hi, 1);
+                const bool bad = (tx.valid && lane > fx && (tx.lo < plo_x || tx.hi < phi_x)) ||
+                                 (ty.valid && lane > fy && (ty.lo < plo_y || ty.hi < phi_y)) ||
+                                 (lane >= fx && lane <= lx && !tx.valid) || (lane >= fy && lane <= ly && !ty.valid) ||
+                                 (tx.valid && (tx.hi < tx.lo || tx.hi > tx.lo + 1)) || (ty.valid && (ty.hi < ty.lo || ty.hi > ty.lo + 1));
+                const bool irregular = __any_sync(full, bad);
+                const unsigned long long rowbytes = (unsigned long long)fw * C * 4ull;
+                if (irregular || fw < 1 || rowbytes > row_cap) mode = 2;
+                // ---- y axis: ordinals of the touched rows ----
+                const int hp_ = (lane == fy) ? -0x40000000 : phi_y;
+                const bool new_lo = ty.valid && ty.lo > hp_;
+                const bool new_hi = ty.valid && ty.hi > ty.lo && ty.hi > hp_;
+                const int cnt = (int)new_lo + (int)new_hi;
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int v = __shfl_up_sync(full, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const int base = incl - cnt;
+                nrows = __shfl_sync(full, incl, 31);
+                int ord_lo = new_lo ? base : base - (hp_ - ty.lo + 1);
+                int ord_hi = new_hi ? base + (int)new_lo : (ty.hi == ty.lo ? ord_lo : base - 1);
+                if (mode == 1) {
+                    if (new_lo) rowy[base] = ty.lo;
+                    if (new_hi) rowy[base + (int)new_lo] = ty.hi;
+                }
+                const unsigned rowpitch = (unsigned)g.W * (unsigned)C * 4u;
+                // per-sample slot values
+                const int ylo_v = !ty.valid ? 0 : (mode == 1 ? ord_lo : (int)((unsigned)ty.lo * rowpitch));
+                const int yhi_v = !ty.valid ? 0 : (mode == 1 ? ord_hi : (int)((unsigned)ty.hi * rowpitch));
+                const unsigned xlo_v = !tx.valid ? 0u : (unsigned)(tx.lo - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
+                const unsigned xhi_v = !tx.valid ? 0u : (unsigned)(tx.hi - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
+                // lane q < PH / PW gathers its two samples (lanes 2q, 2q+1)
+                const int sa = (2 * lane) & 31, sb = (2 * lane + 1) & 31;
+                // y
+                {
+                    const int alo = __shfl_sync(full, ty.lo, sa), ahi = __shfl_sync(full, ty.hi, sa);
+                    const int blo = __shfl_sync(full, ty.lo, sb), bhi = __shfl_sync(full, ty.hi, sb);
+                    const int av = __shfl_sync(full, ty.valid, sa), bv = __shfl_sync(full, ty.valid, sb);
+                    const int a_lo = __shfl_sync(full, ylo_v, sa), a_hi = __shfl_sync(full, yhi_v, sa);
+                    const int b_lo = __shfl_sync(full, ylo_v, sb), b_hi = __shfl_sync(full, yhi_v, sb);
+                    const float ah = __shfl_sync(full, ty.h, sa), al = __shfl_sync(full, ty.l, sa);
+                    const float bh = __shfl_sync(full, ty.h, sb), bl = __shfl_sync(full, ty.l, sb);
+                    const int a_ord_hi = __shfl_sync(full, ord_hi, sa), b_ord_hi = __shfl_sync(full, ord_hi, sb);
+                    // first valid sample after this pooled row -> rows below its low row can be released
+                    const unsigned later = (2 * lane + 2 < 32) ? (ym & ~((1u << (2 * lane + 2)) - 1u)) : 0u;
+                    const int nxt = later ? (__ffs(later) - 1) : 0;
+                    const int nxt_ord = __shfl_sync(full, ord_lo, nxt);
+                    if (lane < PH) {
+                        int pat = 2;
+                        int4 idx = make_int4(a_lo, a_hi, b_lo, b_hi);
+                        if (av && bv && mode == 1) {
+                            if (blo == alo && bhi == ahi) pat = 0;
+                            else if (blo == ahi) { pat = 1; idx.z = b_hi; }
+                        }
+                        const int need = bv ? b_ord_hi + 1 : (av ? a_ord_hi + 1 : 0);
+                        const int rel = later ? nxt_ord : nrows;
+                        G.yidx[lane] = idx;
+                        G.ywa[lane] = make_float4(ah, ah, al, al);
+                        G.ywb[lane] = make_float4(bh, bh, bl, bl);
+                        G.yinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3) | (need << 8) | (rel << 16);
+                    }
+                }
+                // x
+                {
+                    const int alo = __shfl_sync(full, tx.lo, sa), ahi = __shfl_sync(full, tx.hi, sa);
+                    const int blo = __shfl_sync(full, tx.lo, sb), bhi = __shfl_sync(full, tx.hi, sb);
+                    const int av = __shfl_sync(full, tx.valid, sa), bv = __shfl_sync(full, tx.valid, sb);
+                    const unsigned a_lo = __shfl_sync(full, xlo_v, sa), a_hi = __shfl_sync(full, xhi_v, sa);
+                    const unsigned b_lo = __shfl_sync(full, xlo_v, sb), b_hi = __shfl_sync(full, xhi_v, sb);
+                    const float ah = __shfl_sync(full, tx.h, sa), al = __shfl_sync(full, tx.l, sa);
+                    const float bh = __shfl_sync(full, tx.h, sb), bl = __shfl_sync(full, tx.l, sb);
+                    if (lane < PW) {
+                        int pat = 2;
+                        uint4 idx = make_uint4(a_lo, a_hi, b_lo, b_hi);
+                        if (av && bv && mode == 1) {
+                            if (blo == alo && bhi == ahi) pat = 0;
+                            else if (blo == ahi) { pat = 1; idx.z = b_hi; }
+                        }
+                        G.xoff[lane] = idx;
+                        G.xwa[lane] = make_float4(ah, ah, al, al);
+                        G.xwb[lane] = make_float4(bh, bh, bl, bl);
+                        G.xinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3);
+                    }
+                }
+            }
+            const char* img = reinterpret_cast<const char*>(p.features[g.level]) +
+                              (dead ? 0ull : (unsigned long long)g.batch * g.H * g.W * C * 4ull);
+            if (lane == 0) {
+                G.mode = mode;
+                G.seq0 = next_seq;
+                G.nrows = mode == 1 ? nrows : 0;
+                G.img = reinterpret_cast<unsigned long long>(img);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(b_gfull + 8 * par);
+            if (mode != 1) continue;
+            // ---- stream the touched rows into the ring (FIFO byte ring, rows never split) ----
+            const unsigned size = (unsigned)fw * (unsigned)C * 4u;
+            for (int rr = 0; rr < nrows; ++rr) {
+                unsigned off;
+                for (;;) {
+                    if (tail_seq == next_seq) { head = 0; off = 0; break; }      // nothing live
+                    const unsigned tail_off = (unsigned)rowoff[tail_seq & (kRowSlots - 1)];
+                    if (next_seq - tail_seq < kRowSlots) {
+                        if (head > tail_off) {
+                            if (head + size <= ring_bytes) { off = head; break; }
+                            if (size <= tail_off) { off = 0; break; }
+                        } else if (head + size <= tail_off) { off = head; break; }
+                    }
+                    mbar_wait(b_empty + 8 * (tail_seq & (kRowSlots - 1)), (tail_seq >> 6) & 1);   // oldest row released by all consumers
+                    ++tail_seq;
+                }
+                const int slot = next_seq & (kRowSlots - 1);
+                if (lane == 0) {
+                    rowoff[slot] = (int)off;
+                    const char* src = img + ((size_t)rowy[rr] * g.W + x0) * (size_t)C * 4u;
+                    mbar_arrive_expect_tx(b_full + 8 * slot, size);
+                    bulk_g2s(s_base + L.ring + off, src, size, b_full + 8 * slot);
+                }
+                __syncwarp();
+                head = off + size;
+                ++next_seq;
+            }
+        }
+    } else if (warp == kTmaConsumers + 1) {
+        // =========================== store warp: one bulk copy per RoI ===========================
+        int it = 0;
+        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
+            const int b = it & 1;
+            mbar_wait(b_ofull + 8 * b, (it >> 1) & 1);
+            if (lane == 0) {
+                bulk_s2g(out + (size_t)k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the buffer may be rewritten
+                mbar_arrive(b_ofree + 8 * b);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+        // =========================== consumers ===========================
+        const int halves = (C + 127) >> 7;
+        const int T = PW * halves;                    // tasks per pooled row
+        const int rot4 = lane >> 3;
+        int so4[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * nbins;
+        int it = 0;
+        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
+            const int par = it & 1, b = it & 1, u = it >> 1;
+            mbar_wait(b_gfull + 8 * par, u & 1);
+            const TmaGeom& G = geom[par];
+            const int mode = G.mode, seq0 = G.seq0;
+            if (u >= 1) mbar_wait(b_ofree + 8 * b, (u - 1) & 1);
+            float* ob = reinterpret_cast<float*>(smem_raw + L.ob + b * ob_bytes);
+            if (mode == 0) {
+                float4* o4 = reinterpret_cast<float4*>(ob);
+                for (unsigned i = warp * 32 + lane; i < ob_bytes / 16; i += kTmaConsumers * 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                int waited = 0, released = 0;
+                const char* gimg = reinterpret_cast<const char*>(G.img);
+                float2 wx[4];
+                unsigned co[4];
+                int xi = 0, cur_pw = -1;
+                for (int ph = 0; ph < PH; ++ph) {
+                    const int yi = G.yinfo[ph];
+                    const int need = (yi >> 8) & 0xff, rel = (yi >> 16) & 0xff;
+                    if (mode == 1) {
+                        while (waited < need) {
+                            const int s = seq0 + waited;
+                            mbar_wait(b_full + 8 * (s & (kRowSlots - 1)), (s >> 6) & 1);
+                            ++waited;
+                        }
+                    }
+                    const int4 yx = G.yidx[ph];
+                    const float4 ya = G.ywa[ph], yb = G.ywb[ph];
+                    const float2 wy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y),
+                                          make_float2(yb.z, yb.w)};
+                    const int py = yi & 3, yv = (yi >> 2) & 3;
+                    unsigned rs[4];
+                    const char* rg[4];
+                    if (mode == 1) {
+                        const unsigned lb = s_base + L.ring + lane * 16;
+                        const bool a_ok = (yv & 1) != 0, b_ok = (yv & 2) != 0;
+                        // slots of invalid samples are never read; give them the address of slot 0 of the ring
+                        rs[0] = lb + (a_ok ? (unsigned)rowoff[(seq0 + yx.x) & (kRowSlots - 1)] : 0u);
+                        rs[1] = lb + (a_ok ? (unsigned)rowoff[(seq0 + yx.y) & (kRowSlots - 1)] : 0u);
+                        rs[2] = lb + (b_ok ? (unsigned)rowoff[(seq0 + yx.z) & (kRowSlots - 1)] : 0u);
+                        rs[3] = lb + (b_ok ? (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)] : 0u);
+                    } else {
+                        rg[0] = gimg + (unsigned)yx.x + lane * 16;
+                        rg[1] = gimg + (unsigned)yx.y + lane * 16;
+                        rg[2] = gimg + (unsigned)yx.z + lane * 16;
+                        rg[3] = gimg + (unsigned)yx.w + lane * 16;
+                    }
+                    for (int t = warp; t < T; t += kTmaConsumers) {
+                        const int half = t / PW, pw = t - half * PW;
+                        if (pw != cur_pw) {
+                            cur_pw = pw;
+                            const uint4 xo = G.xoff[pw];
+                            const float4 xa = G.xwa[pw], xb = G.xwb[pw];
+                            co[0] = xo.x; co[1] = xo.y; co[2] = xo.z; co[3] = xo.w;
+                            wx[0] = make_float2(xa.x, xa.y); wx[1] = make_float2(xa.z, xa.w);
+                            wx[2] = make_float2(xb.x, xb.y); wx[3] = make_float2(xb.z, xb.w);
+                            xi = G.xinfo[pw];
+                        }
+                        const int c0 = half * 128 + 4 * lane;
+                        if (c0 < C) {
+                            const int px = xi & 3, xv = (xi >> 2) & 3;
+                            const unsigned hoff = (unsigned)half * 512u;
+                            float4 av;
+                            if (mode == 1) {
+                                const unsigned rr[4] = {rs[0] + hoff, rs[1] + hoff, rs[2] + hoff, rs[3] + hoff};
+                                if (yv == 3 && xv == 3) {
+                                    switch (py * 3 + px) {      // warp-uniform
+                                        case 0: av = bin_fast<EXACT, 0, 0>(rr, co, wy, wx, ones); break;
+                                        case 1: av = bin_fast<EXACT, 0, 1>(rr, co, wy, wx, ones); break;
+                                        case 2: av = bin_fast<EXACT, 0, 2>(rr, co, wy, wx, ones); break;
+                                        case 3: av = bin_fast<EXACT, 1, 0>(rr, co, wy, wx, ones); break;
+                                        case 4: av = bin_fast<EXACT, 1, 1>(rr, co, wy, wx, ones); break;
+                                        case 5: av = bin_fast<EXACT, 1, 2>(rr, co, wy, wx, ones); break;
+                                        case 6: av = bin_fast<EXACT, 2, 0>(rr, co, wy, wx, ones); break;
+                                        case 7: av = bin_fast<EXACT, 2, 1>(rr, co, wy, wx, ones); break;
+                                        default: av = bin_fast<EXACT, 2, 2>(rr, co, wy, wx, ones); break;
+                                    }
+                                } else {
+                                    av = bin_generic<EXACT>(rr, co, wy, wx, yv, xv, ones);
+                                }
+                            } else {
+                                const char* rr[4] = {rg[0] + hoff, rg[1] + hoff, rg[2] + hoff, rg[3] + hoff};
+                                av = bin_generic<EXACT>(rr, co, wy, wx, yv, xv, ones);
+                            }
+                            rotate4(av, rot4);
+                            float* o = ob + (size_t)c0 * nbins + ph * PW + pw;
+                            o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
+                        }
+                    }
+                    __syncwarp();
+                    if (mode == 1) {
+                        while (released < rel) {
+                            if (lane == 0) mbar_arrive(b_empty + 8 * ((seq0 + released) & (kRowSlots - 1)));
+                            ++released;
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the bulk copy
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(b_ofull + 8 * b);
+                mbar_arrive(b_gempty + 8 * par);
+            }
+        }
+    }
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+// Launches the TMA kernel if the configuration is inside its envelope; returns 1 if launched, 0 if the caller
+// should take the gather kernel, or a negative/positive error code.
+int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int64_t num_rois, float* out,
+                            int32_t* levels_out, cudaStream_t stream) {
+    static int num_sms = 0, max_smem = 0;
+    static bool attr_set[2] = {false, false};
+    if (num_sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int nbins = p.pooled_h * p.pooled_w;
+    if (!p.channels_last || p.sampling_ratio != 2 || p.aligned || p.channels % 4 || p.pooled_h > kMaxPool ||
+        p.pooled_w > kMaxPool || num_rois >= (1ll << 31))
+        return 0;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return 0;
+    for (int l = 0; l < p.num_levels; ++l) {
+        if ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) != 0) return 0;
+        if ((unsigned long long)p.height[l] * p.width[l] * p.channels * 4ull >= (1ull << 31)) return 0;
+    }
+    const unsigned long long ob = (unsigned long long)p.channels * nbins * 4ull;
+    if (ob % 16 != 0) return 0;
+    const TmaSmem fixed = tma_smem_layout(0, (unsigned)ob);
+    if (ob > (1u << 20) || (long long)max_smem - (long long)fixed.total < 0) return 0;
+    const unsigned ring = ((unsigned)max_smem - fixed.total) / 128u * 128u;
+    const unsigned row_cap = ring / 5u / 16u * 16u;        // 4 rows of one pooled row + the wrap gap always fit
+    if (row_cap < 8u * (unsigned)p.channels * 4u) return 0;   // ring too small to be useful: gather kernel
+    const TmaSmem L = tma_smem_layout(ring, (unsigned)ob);
+    const int grid = (int)(num_rois < num_sms ? num_rois : num_sms);
+    const float2 ones = make_float2(1.0f, 1.0f);
+    const int e = p.exact ? 1 : 0;
+    if (!attr_set[e]) {
+        MB_CUDA(e ? cudaFuncSetAttribute(k_roi_align_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
+                  : cudaFuncSetAttribute(k_roi_align_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        attr_set[e] = true;
+    }
+    if (e)
+        k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones);
+    else
+        k_roi_align_tma<false><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones);
+    MB_LAUNCH_CHECK();
+    return 1;
+}

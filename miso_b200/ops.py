@@ -338,7 +338,7 @@ def convert_boxes_to_roi_format(boxes: Sequence[Tensor]) -> Tensor:
 
 def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence[float], thresholds: Sequence[float],
                       output_size: Tuple[int, int], sampling_ratio: int, aligned: bool, exact: bool,
-                      return_levels: bool = False, use_workspace: bool = True):
+                      return_levels: bool = False, use_workspace: bool = True, force_gather: bool = False):
     lib = _lib.load()
     f0 = features[0]
     k = rois.shape[0]
@@ -357,6 +357,7 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
                 all(f.dtype == torch.float32 and not f.is_contiguous() and
                     f.is_contiguous(memory_format=torch.channels_last) for f in features))
         p.channels_last = int(nhwc)
+        p.force_gather = int(bool(force_gather))
         for i, f in enumerate(features):
             torch._assert(f.shape[0] == n and f.shape[1] == c, "all feature maps must share batch and channel sizes")
             fc = f.detach() if nhwc else _f32c(f)
@@ -375,13 +376,15 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
 
 
 def roi_align(input: Tensor, boxes: Union[Tensor, Sequence[Tensor]], output_size, spatial_scale: float = 1.0,
-              sampling_ratio: int = -1, aligned: bool = False, exact: bool = True) -> Tensor:
-    """RoIAlign forward; `exact=True` reproduces the CPU kernel's fp32 operation order bit for bit."""
+              sampling_ratio: int = -1, aligned: bool = False, exact: bool = True, force_gather: bool = False) -> Tensor:
+    """RoIAlign forward; `exact=True` reproduces the CPU kernel's fp32 operation order bit for bit.
+    `force_gather` keeps channels-last inputs off the TMA-staged kernel (A/B measurements, tests)."""
     _require_cuda(input, "input")
     check_roi_boxes_shape(boxes)
     rois = boxes if isinstance(boxes, Tensor) else convert_boxes_to_roi_format(boxes)
     _require_cuda(rois, "boxes")
-    out = _roi_align_launch([input], _f32c(rois), [spatial_scale], [], _pair(output_size), sampling_ratio, aligned, exact)
+    out = _roi_align_launch([input], _f32c(rois), [spatial_scale], [], _pair(output_size), sampling_ratio, aligned, exact,
+                            force_gather=force_gather)
     return out.to(input.dtype)
 
 
@@ -423,8 +426,9 @@ class MultiScaleRoIAlign(torch.nn.Module):
     constructor and forward(x, boxes, image_shapes); one CUDA launch for all levels."""
 
     def __init__(self, featmap_names: List[str], output_size, sampling_ratio: int, *, canonical_scale: int = 224,
-                 canonical_level: int = 4, exact: bool = True):
+                 canonical_level: int = 4, exact: bool = True, force_gather: bool = False):
         super().__init__()
+        self.force_gather = bool(force_gather)
         self.featmap_names = list(featmap_names)
         self.output_size = _pair(output_size)
         self.sampling_ratio = int(sampling_ratio)
@@ -459,4 +463,4 @@ class MultiScaleRoIAlign(torch.nn.Module):
             self._setup(feats, image_shapes)
         rois = _f32c(convert_boxes_to_roi_format(boxes))
         return _roi_align_launch(feats, rois, self.scales, self.thresholds, self.output_size, self.sampling_ratio,
-                                 False, self.exact, return_levels)
+                                 False, self.exact, return_levels, force_gather=self.force_gather)

@@ -152,10 +152,15 @@ __device__ __forceinline__ float4 bin_fast(const RowT (&rb)[4], const unsigned (
 }
 
 // Any sample may be invalid (skipped like the reference does — no zero-weight multiply, so a NaN/Inf feature
-// never leaks into a bin it does not belong to); slots are the raw (A.lo, A.hi, B.lo, B.hi) of each axis.
+// never leaks into a bin it does not belong to).
+template <typename T>
+__device__ __forceinline__ T slot_sel(const T (&a)[4], int i) {      // a[i] without dynamic register indexing
+    return i == 0 ? a[0] : (i == 1 ? a[1] : (i == 2 ? a[2] : a[3]));
+}
+
 template <bool EXACT, typename RowT>
 __device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&wy)[4],
-                                              const float2 (&wx)[4], int yvalid, int xvalid, float2 ones) {
+                                              const float2 (&wx)[4], int py, int px, int yvalid, int xvalid, float2 ones) {
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
     for (int smp = 0; smp < 4; ++smp) {
@@ -163,8 +168,12 @@ __device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigne
         if (!((yvalid >> iy) & 1) || !((xvalid >> ix) & 1)) continue;       // warp-uniform
         const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
         const float2 w1 = mul2_rn(hyv, hxv), w2 = mul2_rn(hyv, lxv), w3 = mul2_rn(lyv, hxv), w4 = mul2_rn(lyv, lxv);
-        const float4 v1 = tap_ld(rb[2 * iy], co[2 * ix]), v2 = tap_ld(rb[2 * iy], co[2 * ix + 1]);
-        const float4 v3 = tap_ld(rb[2 * iy + 1], co[2 * ix]), v4 = tap_ld(rb[2 * iy + 1], co[2 * ix + 1]);
+        // slots of the second sample follow the axis pattern: (0,1), (1,2) or (2,3)
+        const int ys = iy ? py : 0, xs = ix ? px : 0;
+        const RowT rlo = slot_sel(rb, ys), rhi = slot_sel(rb, ys + 1);
+        const unsigned clo = slot_sel(co, xs), chi = slot_sel(co, xs + 1);
+        const float4 v1 = tap_ld(rlo, clo), v2 = tap_ld(rlo, chi);
+        const float4 v3 = tap_ld(rhi, clo), v4 = tap_ld(rhi, chi);
         lo = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y),
                             make_float2(v4.x, v4.y), lo, ones);
         hi = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w),
@@ -482,11 +491,11 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
                                         default: av = bin_fast<EXACT, 2, 2>(rr, co, wy, wx, ones); break;
                                     }
                                 } else {
-                                    av = bin_generic<EXACT>(rr, co, wy, wx, yv, xv, ones);
+                                    av = bin_generic<EXACT>(rr, co, wy, wx, py, px, yv, xv, ones);
                                 }
                             } else {
                                 const char* rr[4] = {rg[0] + hoff, rg[1] + hoff, rg[2] + hoff, rg[3] + hoff};
-                                av = bin_generic<EXACT>(rr, co, wy, wx, yv, xv, ones);
+                                av = bin_generic<EXACT>(rr, co, wy, wx, py, px, yv, xv, ones);
                             }
                             rotate4(av, rot4);
                             float* o = ob + (size_t)c0 * nbins + ph * PW + pw;

@@ -239,6 +239,26 @@ int mb_mosaic_unpack(const float* block, int64_t rows, float* boxes_out, float* 
                      int64_t* labels_out, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Sparse seam NMS: the same result as mb_nms mode 1 (torchvision's
+ * _batched_nms_vanilla, tv:ops/boxes.py:106-120, CPU kernel arithmetic) over all rows of a gathered block
+ * [rows, 6] = (x1, y1, x2, y2, score, label; label < 0 = ignore), computed on the sparse "may suppress" graph:
+ * rows come in groups of rows_per_tile consecutive rows (one tile's detections) and only rows of tiles whose
+ * bounding boxes intersect are compared. iou_threshold must be >= 0 (MB_ERR_UNSUPPORTED otherwise: with a
+ * negative threshold disjoint boxes suppress each other — use mb_nms). rows_per_tile <= 1024.
+ * state_out [rows] int32: 1 kept, 2 suppressed, 3 ignored row. keep_out (nullable) [rows] int64: kept row
+ * indices ascending. status_out [4] int64: [0] = number kept (0 if keep_out is null) or -1 if edge_capacity was
+ * too small, [1] = suppression edges found (the capacity to retry with).
+ * mb_seam_select: rows [row_lo, row_lo+num_rows) -> boxes [num_rows, 4], scores [num_rows] with -inf for rows
+ * that were not kept: the inputs of mb_crop_plan (one image, capacity num_rows) for a rank's own tiles.
+ * ------------------------------------------------------------------------------------ */
+size_t mb_seam_nms_workspace_bytes(int64_t rows, int32_t rows_per_tile, int64_t edge_capacity);
+int mb_seam_nms(const float* block, int64_t rows, int32_t rows_per_tile, double iou_threshold,
+                int64_t edge_capacity, int32_t* state_out, int64_t* keep_out, int64_t* status_out,
+                void* workspace, size_t workspace_bytes, mb_stream_t stream);
+int mb_seam_select(const float* block, const int32_t* state, int64_t row_lo, int64_t num_rows,
+                   float* boxes_out, float* scores_out, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * paste_masks_in_image (tv:models/detection/roi_heads.py:375-501, called from
  * GeneralizedRCNNTransform.postprocess tv:models/detection/transform.py:269-272).
  * masks [R, 1, M, M] fp32 mask probabilities, boxes [R, 4] fp32 xyxy in image coordinates ->

@@ -103,6 +103,9 @@ SIGNATURES = {
     "mb_crop_gather": (C.c_int, [C.POINTER(CropParams), _p, _p, _p, _p, _p, _i64, _p]),
     "mb_mosaic_pack": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, C.c_float, _i64, _p, _p]),
     "mb_mosaic_unpack": (C.c_int, [_p, _i64, _p, _p, _p, _p]),
+    "mb_seam_nms_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "mb_seam_nms": (C.c_int, [_p, _i64, _i32, _f64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "mb_seam_select": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p]),
     "mb_paste_masks": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
     "mb_image_transform": (C.c_int, [C.POINTER(TransformParams), _p, _p]),
 }

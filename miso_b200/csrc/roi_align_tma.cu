@@ -20,6 +20,8 @@
 //   * the RoI's outputs are collected in shared memory in the output layout [C][PH*PW] (double buffered) and
 //     leave as one bulk async copy issued by the store warp.
 // Every pixel row crosses L2->SM once per RoI, and the loads are decoupled from the arithmetic.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "roi_common.cuh"
 
@@ -203,7 +205,7 @@ __host__ __device__ inline TmaSmem tma_smem_layout(unsigned ring_bytes, unsigned
 template <bool EXACT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __restrict__ rois, int num_rois,
-                float* __restrict__ out, int* __restrict__ levels_out, unsigned ring_bytes, unsigned row_cap, float2 ones) {
+                float* __restrict__ out, int* __restrict__ levels_out, unsigned ring_bytes, unsigned row_cap, float2 ones, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW, C = p.channels;
@@ -382,8 +384,11 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
                 if (lane == 0) {
                     rowoff[slot] = (int)off;
                     const char* src = img + ((size_t)rowy[rr] * g.W + x0) * (size_t)C * 4u;
-                    mbar_arrive_expect_tx(b_full + 8 * slot, size);
-                    bulk_g2s(s_base + L.ring + off, src, size, b_full + 8 * slot);
+                    if (dbg & 1) mbar_arrive(b_full + 8 * slot);          // probe: no copies
+                    else {
+                        mbar_arrive_expect_tx(b_full + 8 * slot, size);
+                        bulk_g2s(s_base + L.ring + off, src, size, b_full + 8 * slot);
+                    }
                 }
                 __syncwarp();
                 head = off + size;
@@ -397,7 +402,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
             const int b = it & 1;
             mbar_wait(b_ofull + 8 * b, (it >> 1) & 1);
             if (lane == 0) {
-                bulk_s2g(out + (size_t)k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);
+                if (!(dbg & 4)) bulk_s2g(out + (size_t)k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);   // probe bit 2: no stores
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the buffer may be rewritten
                 mbar_arrive(b_ofree + 8 * b);
             }
@@ -460,7 +465,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
                         rg[2] = gimg + (unsigned)yx.z + lane * 16;
                         rg[3] = gimg + (unsigned)yx.w + lane * 16;
                     }
-                    for (int t = warp; t < T; t += kTmaConsumers) {
+                    for (int t = warp; t < ((dbg & 2) ? 0 : T); t += kTmaConsumers) {      // probe bit 1: no arithmetic
                         const int half = t / PW, pw = t - half * PW;
                         if (pw != cur_pw) {
                             cur_pw = pw;
@@ -557,15 +562,16 @@ int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int
     const int grid = (int)(num_rois < num_sms ? num_rois : num_sms);
     const float2 ones = make_float2(1.0f, 1.0f);
     const int e = p.exact ? 1 : 0;
+    static const int dbg = getenv("MB_TMA_PROBE") ? atoi(getenv("MB_TMA_PROBE")) : 0;   // development probes, see tools/roi_tma_probe.py
     if (!attr_set[e]) {
         MB_CUDA(e ? cudaFuncSetAttribute(k_roi_align_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
                   : cudaFuncSetAttribute(k_roi_align_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         attr_set[e] = true;
     }
     if (e)
-        k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones);
+        k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones, dbg);
     else
-        k_roi_align_tma<false><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones);
+        k_roi_align_tma<false><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones, dbg);
     MB_LAUNCH_CHECK();
     return 1;
 }

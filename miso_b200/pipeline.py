@@ -45,6 +45,12 @@ class HotPathShapes:
 
 
 class HotPath:
+    # kernels one step() launches, per C-ABI call (checked against the ncu launch list in profiles/)
+    KERNELS = {"mb_rpn_proposals": 7,         # k_rpn_hist, k_rpn_select, k_rpn_decode, k_seg_meta, k_nms_mask, k_nms_sweep_small, k_rpn_finalize
+               "mb_multiscale_roi_align": 1,  # k_roi_align_tma (k_roi_align_nhwc4d outside its envelope)
+               "mb_det_postprocess": 7,       # k_det_init, k_det_candidates, k_seg_meta, k_rank_in_segment, k_nms_mask, k_nms_sweep_small, k_det_finalize
+               "mb_crop_plan": 1, "mb_crop_gather": 1}
+
     def __init__(self, shapes: HotPathShapes, rpn: RpnConfig, det: DetConfig, threshold: float = 0.5,
                  crop_capacity_bytes: int = 64 << 20, exact_roi_align: bool = True, device="cuda:0"):
         self.lib = _lib.load()
@@ -137,7 +143,7 @@ class HotPath:
         self._keep: List[Tensor] = []
         self.roi_ws = None
         self.features_layout = "nchw"
-        self.kernel_launches_per_step = 7 + 1 + 7 + 2   # rpn(6 kernels + sweep), roi_align, det, crop
+        self.kernel_launches_per_step = sum(self.KERNELS.values())
 
     # ------------------------------------------------------------------------------
     def bind(self, objectness: Sequence[Tensor], deltas: Sequence[Tensor], features: Sequence[Tensor],
@@ -161,11 +167,29 @@ class HotPath:
         nb = self.lib.mb_roi_align_workspace_bytes(C.byref(self.roi_params), self.s.num_images * self.R)
         self.roi_ws = torch.empty((nb,), dtype=torch.uint8, device=self.dev) if nb else None
         self.features_layout = "channels_last" if nhwc else "nchw"
-        self.kernel_launches_per_step = 7 + 1 + 7 + 2 + (len(features) if nb else 0)
+        self.kernel_launches_per_step = sum(self.KERNELS.values()) + (len(features) if nb else 0)   # + k_nchw_to_nhwc per level
         for i, im in enumerate(images):
             self.crop_params.images[i] = im.data_ptr()
         self.class_logits, self.box_regression = class_logits, box_regression
         self._graph = None                               # a captured graph refers to the previous tensors
+
+    def rebind(self, objectness: Sequence[Tensor], deltas: Sequence[Tensor], features: Sequence[Tensor],
+               class_logits, box_regression) -> None:
+        """Swap the per-batch inputs (pointers only; shapes, dtypes and memory formats as in the first bind()).
+        Kernel parameters are copied at launch, so this is safe while the previous batch is still running."""
+        if getattr(self, "class_logits", None) is None:
+            dummy = [torch.zeros((1, 1, self.s.image_channels), dtype=torch.uint8, device=self.dev)] * self.s.num_images
+            cl = class_logits[0] if isinstance(class_logits, (list, tuple)) else class_logits
+            br = box_regression[0] if isinstance(box_regression, (list, tuple)) else box_regression
+            self.bind(objectness, deltas, features, cl, br, dummy)
+            return
+        for l, (o, dl) in enumerate(zip(objectness, deltas)):
+            self.rpn_params.objectness[l], self.rpn_params.deltas[l] = o.data_ptr(), dl.data_ptr()
+        for l, f in enumerate(features):
+            self.roi_params.features[l] = f.data_ptr()
+        self.class_logits = class_logits[0] if isinstance(class_logits, (list, tuple)) else class_logits
+        self.box_regression = box_regression[0] if isinstance(box_regression, (list, tuple)) else box_regression
+        self._graph = None
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)

@@ -75,3 +75,81 @@ def faster_rcnn_batch(num_images: int = 4, original: int = 1024, resized: int = 
 def to_device(w: Workload, device) -> Dict[str, List[torch.Tensor]]:
     # .to() keeps the memory format (channels_last stays channels_last)
     return {k: [t.to(device, non_blocking=True) for t in v] for k, v in w.host.items()}
+
+
+# ------------------------------------------------------------------------------------------
+# Config 5: the tiled mosaic. Every tile's head outputs are a function of the tile index alone, so any
+# partition of the tiles over ranks sees the same per-tile inputs (world-size-independent results).
+# ------------------------------------------------------------------------------------------
+@dataclass
+class MosaicWorkload:
+    name: str
+    height: int
+    width: int
+    tile: int
+    overlap: int
+    base: Workload                 # shapes / configs of one tile (num_images = 1)
+    features_layout: str
+
+    def shapes(self, n: int) -> HotPathShapes:
+        s = self.base.shapes
+        return HotPathShapes(num_images=n, padded_image_size=s.padded_image_size, image_sizes=[s.image_sizes[0]] * n,
+                             original_image_sizes=[s.original_image_sizes[0]] * n, rpn_grids=s.rpn_grids,
+                             feature_grids=s.feature_grids, channels=s.channels, num_classes=s.num_classes,
+                             pooled=s.pooled, sampling_ratio=s.sampling_ratio, image_channels=s.image_channels)
+
+    def tile_inputs(self, t: int, device) -> Dict[str, List[torch.Tensor]]:
+        """Seeded (by tile index) head outputs of one tile, generated on `device`."""
+        s = self.base.shapes
+        g = torch.Generator(device=device).manual_seed(7919 * (t + 1))
+        R = self.base.rpn.post_nms_top_n
+
+        def rn(*shape, scale=1.0):
+            return torch.randn(*shape, generator=g, device=device) * scale
+
+        return {
+            "objectness": [rn(1, 3, gh, gw, scale=2.0) for gh, gw in s.rpn_grids],
+            "deltas": [rn(1, 12, gh, gw, scale=0.5) for gh, gw in s.rpn_grids],
+            "features": [rn(1, s.channels, gh, gw) for gh, gw in s.feature_grids],
+            "class_logits": [rn(R, s.num_classes, scale=3.0)],
+            "box_regression": [rn(R, 4 * s.num_classes, scale=0.5)],
+        }
+
+    def batch_inputs(self, tiles: List[int], device) -> Dict[str, List[torch.Tensor]]:
+        """Head outputs of a batch of tiles (concatenated per level; FPN maps in self.features_layout)."""
+        per = [self.tile_inputs(t, device) for t in tiles]
+        out = {k: [torch.cat([p[k][l] for p in per], dim=0).contiguous() for l in range(len(per[0][k]))] for k in per[0]}
+        if self.features_layout == "channels_last":
+            out["features"] = [f.contiguous(memory_format=torch.channels_last) for f in out["features"]]
+        return out
+
+    def band(self, y0: int, y1: int, device) -> torch.Tensor:
+        """Mosaic pixel rows [y0, y1) as uint8 [y1-y0, W, 3]; strips of 128 rows seeded by the strip index, so
+        every rank generates identical pixels for the rows it holds."""
+        strips = []
+        for s0 in range(y0 // 128 * 128, y1, 128):
+            g = torch.Generator(device=device).manual_seed(104729 + s0 // 128)
+            strip = torch.randint(0, 256, (128, self.width, 3), dtype=torch.uint8, generator=g, device=device)
+            strips.append(strip[max(y0 - s0, 0):min(y1 - s0, 128)])
+        return torch.cat(strips, dim=0).contiguous()
+
+    def bytes_per_tile(self) -> int:
+        s = self.base.shapes
+        n = sum(15 * gh * gw for gh, gw in s.rpn_grids) + sum(s.channels * gh * gw for gh, gw in s.feature_grids)
+        return 4 * (n + self.base.rpn.post_nms_top_n * 5 * s.num_classes)
+
+
+def mosaic(height: int = 16384, width: int = 16384, tile: int = 1024, overlap: int = 128, resized: int = 800,
+           channels: int = 256, num_classes: int = 3, post_nms_top_n: int = 1000, detections_per_img: int = 300,
+           threshold: float = 0.5, features_layout: str = "channels_last") -> MosaicWorkload:
+    base = faster_rcnn_batch(num_images=1, original=tile, resized=resized, channels=4, num_classes=num_classes,
+                             post_nms_top_n=post_nms_top_n, detections_per_img=detections_per_img, threshold=threshold,
+                             pin=False)
+    base.shapes.channels = channels
+    base.host = {}
+    from .mosaic import tile_grid
+    nt = len(tile_grid(height, width, tile, overlap))
+    name = (f"config 5: {height}x{width} mosaic, {nt} tiles of {tile} px with {overlap} px overlap, post-head path per tile "
+            f"({tile}^2 -> {resized}^2, {post_nms_top_n} RPN proposals, {channels} ch {features_layout} FPN maps, RoIAlign 7x7, "
+            f"{detections_per_img} dets) + all-gather + seam NMS + crops")
+    return MosaicWorkload(name, height, width, tile, overlap, base, features_layout)

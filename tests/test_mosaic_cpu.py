@@ -1,6 +1,6 @@
-"""Host logic of the tiled-mosaic path without a GPU: tile grid, contiguous rank partition, block
-packing, the one collective (gloo, world_size 2) and the seam-NMS composition. The NMS itself is
-injected (the oracle's per-class strategy) — on the GPU the same code calls libmisob200."""
+"""Host logic of the tiled-mosaic path without a GPU: tile grid, contiguous rank partition, row mapping, pixel
+bands, the one collective (gloo, world_size 2). Packing / seam NMS run here through the CPU restatement of
+tests/mosaic_ref.py (the product has no CPU branch); the GPU tests run the same checks through libmisob200."""
 import os
 import socket
 
@@ -12,6 +12,7 @@ import torch.multiprocessing as mp
 
 from miso_b200 import mosaic
 from oracle import detection as D
+from tests import mosaic_ref as R
 
 
 def test_tile_grid_matches_config5():
@@ -30,10 +31,6 @@ def test_rank_partition_is_contiguous_and_balanced(world):
     assert [i for p in parts for i in p] == list(range(361))
     sizes = [len(p) for p in parts]
     assert max(sizes) - min(sizes) <= 1 and max(sizes) == mosaic.tiles_per_rank_max(361, world)
-
-
-def oracle_nms(boxes, scores, labels, thr):
-    return torch.from_numpy(D.batched_nms_vanilla(boxes.numpy(), scores.numpy(), labels.numpy(), thr))
 
 
 def synth_tiles(num_tiles=5, dpi=40, seed=0):
@@ -57,9 +54,8 @@ def synth_tiles(num_tiles=5, dpi=40, seed=0):
 def single_process(thr=0.5, iou=0.5):
     b, s, l, c, o = synth_tiles()
     T, dpi = s.shape
-    block = mosaic.pack_block(torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(l), torch.from_numpy(c),
-                              torch.from_numpy(o), thr, T * dpi)
-    return mosaic.seam_nms(block, iou, oracle_nms)
+    block = R.pack_block(b, s, l, c, o, thr, T * dpi)
+    return block, R.seam_keep_rows(block, iou)
 
 
 def _worker(rank, world, port, q):
@@ -69,11 +65,10 @@ def _worker(rank, world, port, q):
     T, dpi = s.shape
     mine = list(mosaic.rank_tiles(T, world, rank))
     rows = mosaic.tiles_per_rank_max(T, world) * dpi
-    sel = lambda a: torch.from_numpy(a[mine])
-    block = mosaic.pack_block(sel(b), sel(s), sel(l), sel(c), sel(o), 0.5, rows)
-    gathered = mosaic.exchange(block, world)
-    kb, ks, kl = mosaic.seam_nms(gathered, 0.5, oracle_nms)
-    q.put((rank, kb.numpy(), ks.numpy(), kl.numpy()))
+    block = torch.from_numpy(R.pack_block(b[mine], s[mine], l[mine], c[mine], o[mine], 0.5, rows))
+    gathered = mosaic.exchange(block, world).numpy()          # the product's collective call, gloo backend
+    keep = R.seam_keep_rows(gathered, 0.5)
+    q.put((rank, gathered, keep))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -91,10 +86,14 @@ def test_world_size_2_equals_world_size_1():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    rb, rs, rl = single_process()
-    assert len(rb) < int(synth_tiles()[3].sum())            # the seam duplicates were suppressed
-    for _, kb, ks, kl in res:                               # replicated, deterministic result on every rank
-        assert np.array_equal(kb, rb.numpy()) and np.array_equal(ks, rs.numpy()) and np.array_equal(kl, rl.numpy())
+    block1, keep1 = single_process()
+    T, dpi = synth_tiles()[1].shape
+    assert len(keep1) < int((block1[:, 5] >= 0).sum())        # the seam duplicates were suppressed
+    # world-1 row (tile*dpi + slot) -> row in the 2-rank gathered buffer
+    to2 = np.array([mosaic.gathered_row(r // dpi, r % dpi, T, 2, dpi) for r in range(T * dpi)])
+    for _, gathered, keep in res:                             # replicated, deterministic result on every rank
+        assert np.array_equal(gathered[to2], block1)
+        assert np.array_equal(keep, np.sort(to2[keep1]))
 
 
 def test_seam_nms_matches_reference_composition():
@@ -102,12 +101,27 @@ def test_seam_nms_matches_reference_composition():
     _batched_nms_vanilla -> score filter; the filter commutes with NMS."""
     from torchvision.ops import boxes as tvb
     b, s, l, c, o = synth_tiles()
-    allb, alls, alll = [], [], []
+    T, dpi = s.shape
+    allb, alls, alll, rows = [], [], [], []
     for t in range(len(c)):
         off = np.array([o[t, 1], o[t, 0], o[t, 1], o[t, 0]], np.float32)
         allb.append(b[t, :c[t]] + off); alls.append(s[t, :c[t]]); alll.append(l[t, :c[t]])
+        rows.append(t * dpi + np.arange(c[t]))
     B, S, L = (torch.from_numpy(np.concatenate(x)) for x in (allb, alls, alll))
+    rows = np.concatenate(rows)
     keep = tvb._batched_nms_vanilla(B, S, L, 0.5)
-    keep = keep[S[keep] > 0.5]
-    rb, rs, rl = single_process(0.5, 0.5)
-    assert torch.equal(rb, B[keep]) and torch.equal(rs, S[keep]) and torch.equal(rl, L[keep])
+    keep = keep[S[keep] > 0.5].numpy()
+    block, kept_rows = single_process(0.5, 0.5)
+    assert np.array_equal(np.sort(rows[keep]), kept_rows)
+    assert np.array_equal(block[kept_rows, :4], B.numpy()[np.sort(keep)])
+
+
+def test_rank_bands_cover_own_tiles_only():
+    grid = mosaic.tile_grid(16384, 16384, 1024, 128)
+    for world in (1, 2, 4, 8):
+        for r in range(world):
+            y0, y1 = mosaic.rank_band(grid, 1024, 16384, world, r)
+            for t in mosaic.rank_tiles(len(grid), world, r):
+                assert y0 <= grid[t][0] and grid[t][0] + 1024 <= y1
+            assert (y1 - y0) <= 1024 + 896 * (len(mosaic.rank_tiles(len(grid), world, r)) // 19 + 1)
+    assert mosaic.rank_band(grid, 1024, 16384, 1, 0) == (0, 16384)

@@ -103,12 +103,16 @@ typedef struct {
      * measurements and tests — both produce identical results. */
     int32_t force_gather;
 } mb_roi_align_params;
-/* Optional workspace: when non-zero and provided, NCHW maps are transposed once to channels-last and
- * gathered from there (faster when the RoIs' footprints cover the pyramid several times over). */
+/* Workspace: holds the per-RoI tap-table records of the TMA-staged kernel (channels-last maps, sampling_ratio 2,
+ * aligned = 0) and, for NCHW maps whose RoIs cover the pyramid several times over, one channels-last copy of the
+ * maps (transposed once per call). Without it the call still works and takes the register-gather kernels. */
 size_t mb_roi_align_workspace_bytes(const mb_roi_align_params* params_host, int64_t num_rois);
 int mb_multiscale_roi_align(const mb_roi_align_params* params_host, const float* rois, int64_t num_rois,
                             float* out, int32_t* levels_out /* nullable, [K] */, void* workspace,
                             size_t workspace_bytes, mb_stream_t stream);
+/* Number of calls of this process that took the TMA-staged kernel (k_roi_geom + k_roi_align_tma); the others took
+ * the gather kernels. Lets tests and the bench assert which route produced a result. */
+int64_t mb_roi_align_tma_launches(void);
 
 /* ------------------------------------------------------------------------------------
  * Element-wise box operators.

@@ -89,6 +89,7 @@ SIGNATURES = {
     "mb_nms": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _f64, _p, _p, _p, _sz, _p, _sz, _p]),
     "mb_roi_align_workspace_bytes": (_sz, [C.POINTER(RoiAlignParams), _i64]),
     "mb_multiscale_roi_align": (C.c_int, [C.POINTER(RoiAlignParams), _p, _i64, _p, _p, _p, _sz, _p]),
+    "mb_roi_align_tma_launches": (_i64, []),
     "mb_box_decode": (C.c_int, [_p, _p, _i64, _i32, _f32, _f32, _f32, _f32, _f32, _p, _p]),
     "mb_clip_boxes": (C.c_int, [_p, _i64, _f32, _f32, _p, _p]),
     "mb_box_convert": (C.c_int, [_p, _i64, _i32, _i32, _p, _p]),

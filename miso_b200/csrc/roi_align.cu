@@ -862,7 +862,8 @@ using namespace mb;
 
 // roi_align_tma.cu: 1 = launched, 0 = outside its envelope (take the gather kernel), else an error code
 int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int64_t num_rois, float* out,
-                            int32_t* levels_out, cudaStream_t stream);
+                            int32_t* levels_out, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t mb_roi_align_tma_workspace_bytes(const mb_roi_align_params& p, int64_t num_rois);
 
 static size_t nhwc_copy_bytes(const mb_roi_align_params& p) {
     size_t b = 0;
@@ -871,12 +872,21 @@ static size_t nhwc_copy_bytes(const mb_roi_align_params& p) {
     return b;
 }
 
-// Workspace that lets NCHW inputs take the transpose + channels-last gather route (0 if not applicable).
-extern "C" size_t mb_roi_align_workspace_bytes(const mb_roi_align_params* pp, int64_t num_rois) {
-    if (!pp || pp->channels_last || pp->sampling_ratio != 2 || pp->pooled_h > 16 || pp->pooled_w > 16 || pp->channels % 4) return 0;
+// bytes of the channels-last copies of NCHW maps (0: not applicable / not worth it)
+static size_t nchw_transpose_bytes(const mb_roi_align_params* pp, int64_t num_rois) {
+    if (pp->channels_last || pp->sampling_ratio != 2 || pp->pooled_h > 16 || pp->pooled_w > 16 || pp->channels % 4) return 0;
     const double footprint = (double)num_rois * pp->channels * 320.0 * sizeof(float);   // ~320 pixels per RoI and channel
     const size_t maps = nhwc_copy_bytes(*pp);
     return footprint >= 1.5 * (double)maps ? maps + 256 : 0;
+}
+
+// Workspace: per-RoI tap-table records of the TMA-staged kernel (channels-last maps) and, for NCHW maps whose
+// RoIs cover the pyramid several times over, room for one channels-last copy of the maps.
+extern "C" size_t mb_roi_align_workspace_bytes(const mb_roi_align_params* pp, int64_t num_rois) {
+    if (!pp || num_rois <= 0) return 0;
+    const size_t maps = nchw_transpose_bytes(pp, num_rois);
+    const size_t recs = (pp->channels_last || maps) ? mb_roi_align_tma_workspace_bytes(*pp, num_rois) : 0;
+    return maps + recs;
 }
 
 extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const float* rois, int64_t num_rois,
@@ -899,7 +909,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
                         num_rois * chunks < (1ll << 31);
     if (!p.channels_last && workspace != nullptr && num_rois > 0) {
         // NCHW input with a workspace from mb_roi_align_workspace_bytes: transpose once, gather channels-last
-        const size_t need = mb_roi_align_workspace_bytes(&p, num_rois);
+        const size_t need = nchw_transpose_bytes(&p, num_rois);
         if (need != 0 && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0) {
             char* w = (char*)workspace;
             for (int l = 0; l < p.num_levels; ++l) {
@@ -911,10 +921,12 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
                 w += align_up((size_t)p.num_images * p.channels * HW * sizeof(float), 256);
             }
             p.channels_last = 1;
+            workspace = (char*)workspace + need;      // what is left holds the TMA kernel's records
+            workspace_bytes -= need;
         }
     }
     if (p.channels_last && !p.force_gather) {
-        const int r = mb_launch_roi_align_tma(p, rois, num_rois, out, levels_out, stream);
+        const int r = mb_launch_roi_align_tma(p, rois, num_rois, out, levels_out, workspace, workspace_bytes, stream);
         if (r == 1) return MB_OK;
         if (r != 0) return r;
     }

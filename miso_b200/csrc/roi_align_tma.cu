@@ -7,11 +7,16 @@
 // Why: the gather kernel (k_roi_align_nhwc4d) was latency-bound — each warp had 9 LDG.128 in flight and waited
 // for them (profiles/r1_roi_align_nhwc4d_ncu_full.txt: 35 % resident warps, 42 % of stalls on the first use
 // after the loads) — and pulled every pixel 2.3x through L1 because neighbouring bins share taps. Here
-//   * one CTA per SM (grid = #SMs), RoIs round-robin; 16 warps: 14 consumers, 1 producer, 1 store warp;
-//   * the producer warp builds the RoI's tap tables (lanes = samples) one RoI ahead and streams the touched
-//     pixel rows of the footprint — in channels-last memory a footprint row is ONE contiguous run of
-//     FW*C*4 bytes — with cp.async.bulk (TMA) into a byte ring in shared memory, each row on its own
-//     mbarrier; no registers are held per byte in flight and the copies run ahead across RoI boundaries;
+//   * k_roi_geom (pre-pass, one warp per RoI, lanes = samples) writes every RoI's tap tables — level, footprint,
+//     the list of touched pixel rows, per pooled row / column the distinct taps, weights and sharing pattern —
+//     as one 2 KB record into the workspace: ~5 us of serial geometry per RoI that must not sit on the main
+//     kernel's producer warp (measured: with the geometry inside it, the kernel's skeleton alone took 0.19 ms);
+//   * k_roi_align_tma: one CTA per SM (grid = #SMs), RoIs round-robin; 16 warps: 14 consumers, 1 producer,
+//     1 store warp;
+//   * the producer is a pure TMA issuer: it prefetches the records of the next RoIs (bulk copy, 4-slot ring) and
+//     streams the touched pixel rows of each footprint — in channels-last memory a footprint row is ONE
+//     contiguous run of FW*C*4 bytes — with cp.async.bulk into a byte ring in shared memory, each row on its
+//     own mbarrier; no registers are held per byte in flight and the copies run ahead across RoI boundaries;
 //   * consumer warps walk the pooled rows in order; task = (bin, 128 channels), lane = 4 consecutive channels:
 //     the distinct taps of the bin (3x3 typically) are LDS.128 from the ring, the 16 weight x value products
 //     keep the reference order (exact mode: packed FMUL2 + FFMA2 with an opaque multiplier 1.0f, which is an
@@ -31,13 +36,14 @@ constexpr int kTmaConsumers = 14;
 constexpr int kTmaThreads = (kTmaConsumers + 2) * 32;
 constexpr int kRowSlots = 64;     // row descriptors / barriers in flight
 constexpr int kMaxPool = 16;
+constexpr int kGeomSlots = 4;     // records resident in shared memory (prefetched ahead of the consumers)
 
-struct __align__(16) TmaGeom {
+struct __align__(16) TmaGeom {      // one RoI's tap tables
     int mode;                // 0: zeros, 1: rows staged by TMA, 2: direct global gathers (rows wider than the ring allows)
-    int seq0;                // sequence number of the RoI's first staged row
-    int nrows;               // staged rows
-    int pad;
-    unsigned long long img;  // mode 2: address of the image's map at this level
+    int nrows;               // staged rows (mode 1)
+    unsigned rowbytes;       // bytes of one staged row = footprint width * C * 4
+    int level;
+    unsigned long long img;  // address of the image's map at the RoI's level
     unsigned long long pad2;
     int4 yidx[kMaxPool];     // 4 row slots of a pooled row: ordinals of the staged rows (mode 1) / byte offsets y*W*C*4 (mode 2)
     float4 ywa[kMaxPool];    // (h0, h0, l0, l0)
@@ -47,7 +53,9 @@ struct __align__(16) TmaGeom {
     float4 xwb[kMaxPool];
     int yinfo[kMaxPool];     // pattern (0..2) | valid bits << 2 | rows that must have landed << 8 | rows releasable afterwards << 16
     int xinfo[kMaxPool];     // pattern | valid bits << 2
+    unsigned rowsrc[kRowSlots];   // mode 1: byte offset from img of the first footprint pixel of every staged row
 };
+static_assert(sizeof(TmaGeom) % 16 == 0, "records are moved with bulk copies");
 
 // ---- mbarrier / bulk-copy primitives (PTX) ----
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -187,25 +195,156 @@ __device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigne
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// One warp builds one RoI's record (lanes = samples along each axis).
+__device__ __forceinline__ void build_geom(const mb_roi_align_params& p, const float* __restrict__ rois, int k,
+                                           unsigned row_cap, int lane, TmaGeom& G, int* __restrict__ levels_out) {
+    const unsigned full = 0xffffffffu;
+    const int PH = p.pooled_h, PW = p.pooled_w, C = p.channels;
+    float r[5];
+    load_roi(rois, k, p, r);
+    RoiGeom g;
+    roi_geometry(r, p, g);
+    if (levels_out != nullptr && lane == 0) levels_out[k] = g.level;
+    const bool dead = g.batch < 0 || g.batch >= p.num_images;
+    Tap tx = make_tap(g.start_w, g.bin_w, lane >> 1, lane & 1, 2, g.W);
+    if (lane >= 2 * PW) tx.valid = 0;
+    const unsigned xm = __ballot_sync(full, tx.valid != 0);
+    Tap ty = make_tap(g.start_h, g.bin_h, lane >> 1, lane & 1, 2, g.H);
+    if (lane >= 2 * PH) ty.valid = 0;
+    const unsigned ym = __ballot_sync(full, ty.valid != 0);
+    int mode = (dead || xm == 0 || ym == 0) ? 0 : 1;
+    int x0 = 0, fw = 0, nrows = 0;
+    if (mode != 0) {
+        const int fx = __ffs(xm) - 1, lx = 31 - __clz(xm), fy = __ffs(ym) - 1, ly = 31 - __clz(ym);
+        x0 = __shfl_sync(full, tx.lo, fx);
+        fw = __shfl_sync(full, tx.hi, lx) - x0 + 1;
+        // valid samples must be one run with non-decreasing pixel indices (bin size > 0 guarantees it);
+        // anything else takes the direct route, which does not rely on it
+        const int plo_x = __shfl_up_sync(full, tx.lo, 1), plo_y = __shfl_up_sync(full, ty.lo, 1);
+        const int phi_x = __shfl_up_sync(full, tx.hi, 1), phi_y = __shfl_up_sync(full, ty.hi, 1);
+        const bool bad = (tx.valid && lane > fx && (tx.lo < plo_x || tx.hi < phi_x)) ||
+                         (ty.valid && lane > fy && (ty.lo < plo_y || ty.hi < phi_y)) ||
+                         (lane >= fx && lane <= lx && !tx.valid) || (lane >= fy && lane <= ly && !ty.valid) ||
+                         (tx.valid && (tx.hi < tx.lo || tx.hi > tx.lo + 1)) || (ty.valid && (ty.hi < ty.lo || ty.hi > ty.lo + 1));
+        const bool irregular = __any_sync(full, bad);
+        const unsigned long long rowbytes = (unsigned long long)fw * C * 4ull;
+        if (irregular || fw < 1 || rowbytes > row_cap) mode = 2;
+        // ---- y axis: ordinals of the touched rows ----
+        const int hp_ = (lane == fy) ? -0x40000000 : phi_y;
+        const bool new_lo = ty.valid && ty.lo > hp_;
+        const bool new_hi = ty.valid && ty.hi > ty.lo && ty.hi > hp_;
+        const int cnt = (int)new_lo + (int)new_hi;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(full, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const int base = incl - cnt;
+        nrows = __shfl_sync(full, incl, 31);
+        const int ord_lo = new_lo ? base : base - (hp_ - ty.lo + 1);
+        const int ord_hi = new_hi ? base + (int)new_lo : (ty.hi == ty.lo ? ord_lo : base - 1);
+        if (mode == 1) {      // byte offset of the row's first footprint pixel
+            if (new_lo) G.rowsrc[base] = ((unsigned)ty.lo * (unsigned)g.W + (unsigned)x0) * (unsigned)C * 4u;
+            if (new_hi) G.rowsrc[base + (int)new_lo] = ((unsigned)ty.hi * (unsigned)g.W + (unsigned)x0) * (unsigned)C * 4u;
+        }
+        const unsigned rowpitch = (unsigned)g.W * (unsigned)C * 4u;
+        // per-sample slot values
+        const int ylo_v = !ty.valid ? 0 : (mode == 1 ? ord_lo : (int)((unsigned)ty.lo * rowpitch));
+        const int yhi_v = !ty.valid ? 0 : (mode == 1 ? ord_hi : (int)((unsigned)ty.hi * rowpitch));
+        const unsigned xlo_v = !tx.valid ? 0u : (unsigned)(tx.lo - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
+        const unsigned xhi_v = !tx.valid ? 0u : (unsigned)(tx.hi - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
+        // lane q < PH / PW gathers its two samples (lanes 2q, 2q+1)
+        const int sa = (2 * lane) & 31, sb = (2 * lane + 1) & 31;
+        {   // y
+            const int alo = __shfl_sync(full, ty.lo, sa), ahi = __shfl_sync(full, ty.hi, sa);
+            const int blo = __shfl_sync(full, ty.lo, sb), bhi = __shfl_sync(full, ty.hi, sb);
+            const int av = __shfl_sync(full, ty.valid, sa), bv = __shfl_sync(full, ty.valid, sb);
+            const int a_lo = __shfl_sync(full, ylo_v, sa), a_hi = __shfl_sync(full, yhi_v, sa);
+            const int b_lo = __shfl_sync(full, ylo_v, sb), b_hi = __shfl_sync(full, yhi_v, sb);
+            const float ah = __shfl_sync(full, ty.h, sa), al = __shfl_sync(full, ty.l, sa);
+            const float bh = __shfl_sync(full, ty.h, sb), bl = __shfl_sync(full, ty.l, sb);
+            const int a_ord_hi = __shfl_sync(full, ord_hi, sa), b_ord_hi = __shfl_sync(full, ord_hi, sb);
+            // first valid sample after this pooled row -> rows below its low row can be released
+            const unsigned later = (2 * lane + 2 < 32) ? (ym & ~((1u << (2 * lane + 2)) - 1u)) : 0u;
+            const int nxt = later ? (__ffs(later) - 1) : 0;
+            const int nxt_ord = __shfl_sync(full, ord_lo, nxt);
+            if (lane < PH) {
+                int pat = 2;
+                int4 idx = make_int4(a_lo, a_hi, b_lo, b_hi);
+                if (av && bv && mode == 1) {
+                    if (blo == alo && bhi == ahi) pat = 0;
+                    else if (blo == ahi) { pat = 1; idx.z = b_hi; }
+                }
+                const int need = bv ? b_ord_hi + 1 : (av ? a_ord_hi + 1 : 0);
+                const int rel = later ? nxt_ord : nrows;
+                G.yidx[lane] = idx;
+                G.ywa[lane] = make_float4(ah, ah, al, al);
+                G.ywb[lane] = make_float4(bh, bh, bl, bl);
+                G.yinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3) | (need << 8) | (rel << 16);
+            }
+        }
+        {   // x
+            const int alo = __shfl_sync(full, tx.lo, sa), ahi = __shfl_sync(full, tx.hi, sa);
+            const int blo = __shfl_sync(full, tx.lo, sb), bhi = __shfl_sync(full, tx.hi, sb);
+            const int av = __shfl_sync(full, tx.valid, sa), bv = __shfl_sync(full, tx.valid, sb);
+            const unsigned a_lo = __shfl_sync(full, xlo_v, sa), a_hi = __shfl_sync(full, xhi_v, sa);
+            const unsigned b_lo = __shfl_sync(full, xlo_v, sb), b_hi = __shfl_sync(full, xhi_v, sb);
+            const float ah = __shfl_sync(full, tx.h, sa), al = __shfl_sync(full, tx.l, sa);
+            const float bh = __shfl_sync(full, tx.h, sb), bl = __shfl_sync(full, tx.l, sb);
+            if (lane < PW) {
+                int pat = 2;
+                uint4 idx = make_uint4(a_lo, a_hi, b_lo, b_hi);
+                if (av && bv && mode == 1) {
+                    if (blo == alo && bhi == ahi) pat = 0;
+                    else if (blo == ahi) { pat = 1; idx.z = b_hi; }
+                }
+                G.xoff[lane] = idx;
+                G.xwa[lane] = make_float4(ah, ah, al, al);
+                G.xwb[lane] = make_float4(bh, bh, bl, bl);
+                G.xinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3);
+            }
+        }
+    }
+    const char* img = reinterpret_cast<const char*>(p.features[g.level]) +
+                      (dead ? 0ull : (unsigned long long)g.batch * g.H * g.W * C * 4ull);
+    if (lane == 0) {
+        G.mode = mode;
+        G.nrows = mode == 1 ? nrows : 0;
+        G.rowbytes = (unsigned)fw * (unsigned)C * 4u;
+        G.level = g.level;
+        G.img = reinterpret_cast<unsigned long long>(img);
+        G.pad2 = 0;
+    }
+}
+
+// Pre-pass: the tap tables of every RoI, one warp each, written to the workspace.
+__global__ void __launch_bounds__(256) k_roi_geom(const __grid_constant__ mb_roi_align_params p, const float* __restrict__ rois,
+                                                 int num_rois, unsigned row_cap, TmaGeom* __restrict__ recs,
+                                                 int* __restrict__ levels_out) {
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (k >= num_rois) return;
+    build_geom(p, rois, k, row_cap, threadIdx.x & 31, recs[k], levels_out);
+}
+
 struct TmaSmem {          // carve-up of the dynamic shared memory (offsets in bytes)
-    unsigned ring, ob, geom, rowoff, rowy, bars, total;
+    unsigned ring, ob, geom, rowoff, bars, total;
 };
 __host__ __device__ inline TmaSmem tma_smem_layout(unsigned ring_bytes, unsigned ob_bytes) {
     TmaSmem s;
     s.ring = 0;
     s.ob = ring_bytes;
     s.geom = s.ob + 2 * ob_bytes;
-    s.rowoff = s.geom + 2 * (unsigned)sizeof(TmaGeom);
-    s.rowy = s.rowoff + kRowSlots * 4;
-    s.bars = s.rowy + kRowSlots * 4;
-    s.total = s.bars + (2 * kRowSlots + 8) * 8;
+    s.rowoff = s.geom + kGeomSlots * (unsigned)sizeof(TmaGeom);
+    s.bars = s.rowoff + kRowSlots * 4;
+    s.total = s.bars + (2 * kRowSlots + 2 * kGeomSlots + 4) * 8;
     return s;
 }
 
 template <bool EXACT>
 __global__ void __launch_bounds__(kTmaThreads, 1)
-k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __restrict__ rois, int num_rois,
-                float* __restrict__ out, int* __restrict__ levels_out, unsigned ring_bytes, unsigned row_cap, float2 ones, int dbg) {
+k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __restrict__ recs, int num_rois,
+                float* __restrict__ out, unsigned ring_bytes, float2 ones, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int PH = p.pooled_h, PW = p.pooled_w, nbins = PH * PW, C = p.channels;
@@ -213,19 +352,20 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
     const TmaSmem L = tma_smem_layout(ring_bytes, ob_bytes);
     TmaGeom* geom = reinterpret_cast<TmaGeom*>(smem_raw + L.geom);
     volatile int* rowoff = reinterpret_cast<volatile int*>(smem_raw + L.rowoff);
-    int* rowy = reinterpret_cast<int*>(smem_raw + L.rowy);
     const unsigned s_base = smem_u32(smem_raw);
     const unsigned b_full = s_base + L.bars, b_empty = b_full + kRowSlots * 8, b_gfull = b_empty + kRowSlots * 8;
-    const unsigned b_gempty = b_gfull + 16, b_ofull = b_gempty + 16, b_ofree = b_ofull + 16;
+    const unsigned b_gempty = b_gfull + kGeomSlots * 8, b_ofull = b_gempty + kGeomSlots * 8, b_ofree = b_ofull + 16;
 
     if (tid == 0) {
         for (int i = 0; i < kRowSlots; ++i) {
             mbar_init(b_full + 8 * i, 1);
             mbar_init(b_empty + 8 * i, kTmaConsumers);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kGeomSlots; ++i) {
             mbar_init(b_gfull + 8 * i, 1);
             mbar_init(b_gempty + 8 * i, kTmaConsumers);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(b_ofull + 8 * i, kTmaConsumers);
             mbar_init(b_ofree + 8 * i, 1);
         }
@@ -233,139 +373,37 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    const int my_rois = blockIdx.x < num_rois ? (num_rois - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    const unsigned full = 0xffffffffu;
     if (warp == kTmaConsumers) {
-        // =========================== producer: tap tables + TMA row copies ===========================
+        // =========================== producer: record prefetch + TMA row copies ===========================
         int next_seq = 0, tail_seq = 0;
         unsigned head = 0;
-        int it = 0;
-        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
-            const int par = it & 1;
-            if (it >= 2) mbar_wait(b_gempty + 8 * par, ((it >> 1) - 1) & 1);
-            TmaGeom& G = geom[par];
-            float r[5];
-            load_roi(rois, k, p, r);
-            RoiGeom g;
-            roi_geometry(r, p, g);
-            if (levels_out != nullptr && lane == 0) levels_out[k] = g.level;
-            const bool dead = g.batch < 0 || g.batch >= p.num_images;
-            // ---- x axis ----
-            Tap tx = make_tap(g.start_w, g.bin_w, lane >> 1, lane & 1, 2, g.W);
-            if (lane >= 2 * PW) tx.valid = 0;
-            const unsigned xm = __ballot_sync(full, tx.valid != 0);
-            Tap ty = make_tap(g.start_h, g.bin_h, lane >> 1, lane & 1, 2, g.H);
-            if (lane >= 2 * PH) ty.valid = 0;
-            const unsigned ym = __ballot_sync(full, ty.valid != 0);
-            int mode = (dead || xm == 0 || ym == 0) ? 0 : 1;
-            int x0 = 0, fw = 0, nrows = 0;
-            if (mode != 0) {
-                const int fx = __ffs(xm) - 1, lx = 31 - __clz(xm), fy = __ffs(ym) - 1, ly = 31 - __clz(ym);
-                x0 = __shfl_sync(full, tx.lo, fx);
-                fw = __shfl_sync(full, tx.hi, lx) - x0 + 1;
-                // valid samples must be one run with non-decreasing pixel indices (bin size > 0 guarantees it);
-                // anything else takes the direct route, which does not rely on it
-                const int plo_x = __shfl_up_sync(full, tx.lo, 1), plo_y = __shfl_up_sync(full, ty.lo, 1);
-                const int phi_x = __shfl_up_sync(full, tx.hi, 1), phi_y = __shfl_up_sync(full, ty.hi, 1);
-                const bool bad = (tx.valid && lane > fx && (tx.lo < plo_x || tx.hi < phi_x)) ||
-                                 (ty.valid && lane > fy && (ty.lo < plo_y || ty.hi < phi_y)) ||
-                                 (lane >= fx && lane <= lx && !tx.valid) || (lane >= fy && lane <= ly && !ty.valid) ||
-                                 (tx.valid && (tx.hi < tx.lo || tx.hi > tx.lo + 1)) || (ty.valid && (ty.hi < ty.lo || ty.hi > ty.lo + 1));
-                const bool irregular = __any_sync(full, bad);
-                const unsigned long long rowbytes = (unsigned long long)fw * C * 4ull;
-                if (irregular || fw < 1 || rowbytes > row_cap) mode = 2;
-                // ---- y axis: ordinals of the touched rows ----
-                const int hp_ = (lane == fy) ? -0x40000000 : phi_y;
-                const bool new_lo = ty.valid && ty.lo > hp_;
-                const bool new_hi = ty.valid && ty.hi > ty.lo && ty.hi > hp_;
-                const int cnt = (int)new_lo + (int)new_hi;
-                int incl = cnt;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int v = __shfl_up_sync(full, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                const int base = incl - cnt;
-                nrows = __shfl_sync(full, incl, 31);
-                int ord_lo = new_lo ? base : base - (hp_ - ty.lo + 1);
-                int ord_hi = new_hi ? base + (int)new_lo : (ty.hi == ty.lo ? ord_lo : base - 1);
-                if (mode == 1) {
-                    if (new_lo) rowy[base] = ty.lo;
-                    if (new_hi) rowy[base + (int)new_lo] = ty.hi;
-                }
-                const unsigned rowpitch = (unsigned)g.W * (unsigned)C * 4u;
-                // per-sample slot values
-                const int ylo_v = !ty.valid ? 0 : (mode == 1 ? ord_lo : (int)((unsigned)ty.lo * rowpitch));
-                const int yhi_v = !ty.valid ? 0 : (mode == 1 ? ord_hi : (int)((unsigned)ty.hi * rowpitch));
-                const unsigned xlo_v = !tx.valid ? 0u : (unsigned)(tx.lo - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
-                const unsigned xhi_v = !tx.valid ? 0u : (unsigned)(tx.hi - (mode == 1 ? x0 : 0)) * (unsigned)C * 4u;
-                // lane q < PH / PW gathers its two samples (lanes 2q, 2q+1)
-                const int sa = (2 * lane) & 31, sb = (2 * lane + 1) & 31;
-                // y
-                {
-                    const int alo = __shfl_sync(full, ty.lo, sa), ahi = __shfl_sync(full, ty.hi, sa);
-                    const int blo = __shfl_sync(full, ty.lo, sb), bhi = __shfl_sync(full, ty.hi, sb);
-                    const int av = __shfl_sync(full, ty.valid, sa), bv = __shfl_sync(full, ty.valid, sb);
-                    const int a_lo = __shfl_sync(full, ylo_v, sa), a_hi = __shfl_sync(full, yhi_v, sa);
-                    const int b_lo = __shfl_sync(full, ylo_v, sb), b_hi = __shfl_sync(full, yhi_v, sb);
-                    const float ah = __shfl_sync(full, ty.h, sa), al = __shfl_sync(full, ty.l, sa);
-                    const float bh = __shfl_sync(full, ty.h, sb), bl = __shfl_sync(full, ty.l, sb);
-                    const int a_ord_hi = __shfl_sync(full, ord_hi, sa), b_ord_hi = __shfl_sync(full, ord_hi, sb);
-                    // first valid sample after this pooled row -> rows below its low row can be released
-                    const unsigned later = (2 * lane + 2 < 32) ? (ym & ~((1u << (2 * lane + 2)) - 1u)) : 0u;
-                    const int nxt = later ? (__ffs(later) - 1) : 0;
-                    const int nxt_ord = __shfl_sync(full, ord_lo, nxt);
-                    if (lane < PH) {
-                        int pat = 2;
-                        int4 idx = make_int4(a_lo, a_hi, b_lo, b_hi);
-                        if (av && bv && mode == 1) {
-                            if (blo == alo && bhi == ahi) pat = 0;
-                            else if (blo == ahi) { pat = 1; idx.z = b_hi; }
-                        }
-                        const int need = bv ? b_ord_hi + 1 : (av ? a_ord_hi + 1 : 0);
-                        const int rel = later ? nxt_ord : nrows;
-                        G.yidx[lane] = idx;
-                        G.ywa[lane] = make_float4(ah, ah, al, al);
-                        G.ywb[lane] = make_float4(bh, bh, bl, bl);
-                        G.yinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3) | (need << 8) | (rel << 16);
-                    }
-                }
-                // x
-                {
-                    const int alo = __shfl_sync(full, tx.lo, sa), ahi = __shfl_sync(full, tx.hi, sa);
-                    const int blo = __shfl_sync(full, tx.lo, sb), bhi = __shfl_sync(full, tx.hi, sb);
-                    const int av = __shfl_sync(full, tx.valid, sa), bv = __shfl_sync(full, tx.valid, sb);
-                    const unsigned a_lo = __shfl_sync(full, xlo_v, sa), a_hi = __shfl_sync(full, xhi_v, sa);
-                    const unsigned b_lo = __shfl_sync(full, xlo_v, sb), b_hi = __shfl_sync(full, xhi_v, sb);
-                    const float ah = __shfl_sync(full, tx.h, sa), al = __shfl_sync(full, tx.l, sa);
-                    const float bh = __shfl_sync(full, tx.h, sb), bl = __shfl_sync(full, tx.l, sb);
-                    if (lane < PW) {
-                        int pat = 2;
-                        uint4 idx = make_uint4(a_lo, a_hi, b_lo, b_hi);
-                        if (av && bv && mode == 1) {
-                            if (blo == alo && bhi == ahi) pat = 0;
-                            else if (blo == ahi) { pat = 1; idx.z = b_hi; }
-                        }
-                        G.xoff[lane] = idx;
-                        G.xwa[lane] = make_float4(ah, ah, al, al);
-                        G.xwb[lane] = make_float4(bh, bh, bl, bl);
-                        G.xinfo[lane] = pat | ((av ? 1 : 0) << 2) | ((bv ? 1 : 0) << 3);
-                    }
-                }
-            }
-            const char* img = reinterpret_cast<const char*>(p.features[g.level]) +
-                              (dead ? 0ull : (unsigned long long)g.batch * g.H * g.W * C * 4ull);
+        auto fetch_record = [&](int j) {          // record of this CTA's j-th RoI -> slot j % kGeomSlots
+            if (j >= my_rois) return;
+            const int slot = j % kGeomSlots, use = j / kGeomSlots;
+            if (use >= 1) mbar_wait(b_gempty + 8 * slot, (use - 1) & 1);        // consumers are done with the slot's previous record
             if (lane == 0) {
-                G.mode = mode;
-                G.seq0 = next_seq;
-                G.nrows = mode == 1 ? nrows : 0;
-                G.img = reinterpret_cast<unsigned long long>(img);
+                mbar_arrive_expect_tx(b_gfull + 8 * slot, (unsigned)sizeof(TmaGeom));
+                bulk_g2s(s_base + L.geom + slot * (unsigned)sizeof(TmaGeom), recs + (blockIdx.x + (size_t)j * gridDim.x),
+                         (unsigned)sizeof(TmaGeom), b_gfull + 8 * slot);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(b_gfull + 8 * par);
-            if (mode != 1) continue;
+        };
+        // Records are fetched two RoIs ahead into a 4-slot ring: the slot reused at iteration `it` held RoI it-2,
+        // which the consumers finished long ago (the row ring only lets the producer run ~one RoI ahead), so this
+        // wait never stalls the row stream.
+        for (int j = 0; j < kGeomSlots - 2; ++j) fetch_record(j);
+        for (int it = 0; it < my_rois; ++it) {
+            fetch_record(it + kGeomSlots - 2);
+            const int gs = it % kGeomSlots;
+            mbar_wait(b_gfull + 8 * gs, (it / kGeomSlots) & 1);
+            const TmaGeom& G = geom[gs];
+            if (G.mode != 1) continue;
+            const int nrows = G.nrows;
+            const unsigned size = G.rowbytes;
+            const char* img = reinterpret_cast<const char*>(G.img);
             // ---- stream the touched rows into the ring (FIFO byte ring, rows never split) ----
-            const unsigned size = (unsigned)fw * (unsigned)C * 4u;
             for (int rr = 0; rr < nrows; ++rr) {
                 unsigned off;
                 for (;;) {
@@ -383,11 +421,10 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
                 const int slot = next_seq & (kRowSlots - 1);
                 if (lane == 0) {
                     rowoff[slot] = (int)off;
-                    const char* src = img + ((size_t)rowy[rr] * g.W + x0) * (size_t)C * 4u;
                     if (dbg & 1) mbar_arrive(b_full + 8 * slot);          // probe: no copies
                     else {
                         mbar_arrive_expect_tx(b_full + 8 * slot, size);
-                        bulk_g2s(s_base + L.ring + off, src, size, b_full + 8 * slot);
+                        bulk_g2s(s_base + L.ring + off, img + G.rowsrc[rr], size, b_full + 8 * slot);
                     }
                 }
                 __syncwarp();
@@ -397,12 +434,12 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
         }
     } else if (warp == kTmaConsumers + 1) {
         // =========================== store warp: one bulk copy per RoI ===========================
-        int it = 0;
-        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
+        for (int it = 0; it < my_rois; ++it) {
             const int b = it & 1;
+            const size_t k = blockIdx.x + (size_t)it * gridDim.x;
             mbar_wait(b_ofull + 8 * b, (it >> 1) & 1);
             if (lane == 0) {
-                if (!(dbg & 4)) bulk_s2g(out + (size_t)k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);   // probe bit 2: no stores
+                if (!(dbg & 4)) bulk_s2g(out + k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);   // probe bit 2: no stores
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the buffer may be rewritten
                 mbar_arrive(b_ofree + 8 * b);
             }
@@ -417,12 +454,12 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
         int so4[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * nbins;
-        int it = 0;
-        for (int k = blockIdx.x; k < num_rois; k += gridDim.x, ++it) {
-            const int par = it & 1, b = it & 1, u = it >> 1;
-            mbar_wait(b_gfull + 8 * par, u & 1);
-            const TmaGeom& G = geom[par];
-            const int mode = G.mode, seq0 = G.seq0;
+        int seq0 = 0;                                 // sequence number of the current RoI's first staged row
+        for (int it = 0; it < my_rois; ++it) {
+            const int gs = it % kGeomSlots, b = it & 1, u = it >> 1;
+            mbar_wait(b_gfull + 8 * gs, (it / kGeomSlots) & 1);
+            const TmaGeom& G = geom[gs];
+            const int mode = G.mode, nrows = G.nrows;
             if (u >= 1) mbar_wait(b_ofree + 8 * b, (u - 1) & 1);
             float* ob = reinterpret_cast<float*>(smem_raw + L.ob + b * ob_bytes);
             if (mode == 0) {
@@ -515,12 +552,13 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
                         }
                     }
                 }
+                seq0 += nrows;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the bulk copy
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(b_ofull + 8 * b);
-                mbar_arrive(b_gempty + 8 * par);
+                mbar_arrive(b_gempty + 8 * gs);
             }
         }
     }
@@ -530,48 +568,68 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const float* __re
 
 using namespace mb;
 
-// Launches the TMA kernel if the configuration is inside its envelope; returns 1 if launched, 0 if the caller
-// should take the gather kernel, or a negative/positive error code.
-int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int64_t num_rois, float* out,
-                            int32_t* levels_out, cudaStream_t stream) {
-    static int num_sms = 0, max_smem = 0;
-    static bool attr_set[2] = {false, false};
-    if (num_sms == 0) {
+static int g_tma_sms = 0, g_tma_smem = 0;
+static long long g_tma_launches = 0;
+extern "C" int64_t mb_roi_align_tma_launches(void) { return g_tma_launches; }
+static bool tma_device_info() {
+    if (g_tma_sms == 0) {
         int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&g_tma_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&g_tma_sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int nbins = p.pooled_h * p.pooled_w;
-    if (!p.channels_last || p.sampling_ratio != 2 || p.aligned || p.channels % 4 || p.pooled_h > kMaxPool ||
-        p.pooled_w > kMaxPool || num_rois >= (1ll << 31))
-        return 0;
+    return g_tma_sms > 0;
+}
+
+// static part of the envelope (no device query): what mb_roi_align_workspace_bytes can decide
+static bool tma_shape_ok(const mb_roi_align_params& p, int64_t num_rois) {
+    const long long ob = (long long)p.channels * p.pooled_h * p.pooled_w * 4ll;
+    return p.sampling_ratio == 2 && !p.aligned && p.channels % 4 == 0 && p.pooled_h >= 1 && p.pooled_w >= 1 &&
+           p.pooled_h <= kMaxPool && p.pooled_w <= kMaxPool && num_rois > 0 && num_rois < (1ll << 31) && ob % 16 == 0 &&
+           2 * ob <= 112 * 1024;
+}
+
+// bytes of workspace the TMA route needs for its per-RoI records (0: outside the envelope)
+size_t mb_roi_align_tma_workspace_bytes(const mb_roi_align_params& p, int64_t num_rois) {
+    return tma_shape_ok(p, num_rois) ? (size_t)num_rois * sizeof(TmaGeom) + 256 : 0;
+}
+
+// Launches the pre-pass + the TMA kernel if the configuration is inside the envelope and the workspace holds the
+// records; returns 1 if launched, 0 if the caller should take the gather kernel, or an error code.
+int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int64_t num_rois, float* out,
+                            int32_t* levels_out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    static bool attr_set[2] = {false, false};
+    if (!p.channels_last || !tma_shape_ok(p, num_rois) || !tma_device_info()) return 0;
+    if (workspace == nullptr || workspace_bytes < mb_roi_align_tma_workspace_bytes(p, num_rois)) return 0;
     if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return 0;
     for (int l = 0; l < p.num_levels; ++l) {
         if ((reinterpret_cast<uintptr_t>(p.features[l]) & 15) != 0) return 0;
         if ((unsigned long long)p.height[l] * p.width[l] * p.channels * 4ull >= (1ull << 31)) return 0;
     }
-    const unsigned long long ob = (unsigned long long)p.channels * nbins * 4ull;
-    if (ob % 16 != 0) return 0;
-    const TmaSmem fixed = tma_smem_layout(0, (unsigned)ob);
-    if (ob > (1u << 20) || (long long)max_smem - (long long)fixed.total < 0) return 0;
-    const unsigned ring = ((unsigned)max_smem - fixed.total) / 128u * 128u;
+    const unsigned ob = (unsigned)p.channels * p.pooled_h * p.pooled_w * 4u;
+    const TmaSmem fixed = tma_smem_layout(0, ob);
+    if ((long long)g_tma_smem - (long long)fixed.total <= 0) return 0;
+    const unsigned ring = ((unsigned)g_tma_smem - fixed.total) / 128u * 128u;
     const unsigned row_cap = ring / 5u / 16u * 16u;        // 4 rows of one pooled row + the wrap gap always fit
     if (row_cap < 8u * (unsigned)p.channels * 4u) return 0;   // ring too small to be useful: gather kernel
-    const TmaSmem L = tma_smem_layout(ring, (unsigned)ob);
-    const int grid = (int)(num_rois < num_sms ? num_rois : num_sms);
+    const TmaSmem L = tma_smem_layout(ring, ob);
+    TmaGeom* recs = reinterpret_cast<TmaGeom*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+    const int grid = (int)(num_rois < g_tma_sms ? num_rois : g_tma_sms);
     const float2 ones = make_float2(1.0f, 1.0f);
     const int e = p.exact ? 1 : 0;
     static const int dbg = getenv("MB_TMA_PROBE") ? atoi(getenv("MB_TMA_PROBE")) : 0;   // development probes, see tools/roi_tma_probe.py
     if (!attr_set[e]) {
-        MB_CUDA(e ? cudaFuncSetAttribute(k_roi_align_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)
-                  : cudaFuncSetAttribute(k_roi_align_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        MB_CUDA(e ? cudaFuncSetAttribute(k_roi_align_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_smem)
+                  : cudaFuncSetAttribute(k_roi_align_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_smem));
         attr_set[e] = true;
     }
-    if (e)
-        k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones, dbg);
-    else
-        k_roi_align_tma<false><<<grid, kTmaThreads, L.total, stream>>>(p, rois, (int)num_rois, out, levels_out, ring, row_cap, ones, dbg);
+    k_roi_geom<<<(unsigned)((num_rois + 7) / 8), 256, 0, stream>>>(p, rois, (int)num_rois, row_cap, recs, levels_out);
     MB_LAUNCH_CHECK();
+    if (e)
+        k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, recs, (int)num_rois, out, ring, ones, dbg);
+    else
+        k_roi_align_tma<false><<<grid, kTmaThreads, L.total, stream>>>(p, recs, (int)num_rois, out, ring, ones, dbg);
+    MB_LAUNCH_CHECK();
+    ++g_tma_launches;
     return 1;
 }

@@ -47,7 +47,7 @@ class HotPathShapes:
 class HotPath:
     # kernels one step() launches, per C-ABI call (checked against the ncu launch list in profiles/)
     KERNELS = {"mb_rpn_proposals": 7,         # k_rpn_hist, k_rpn_select, k_rpn_decode, k_seg_meta, k_nms_mask, k_nms_sweep_small, k_rpn_finalize
-               "mb_multiscale_roi_align": 1,  # k_roi_align_tma (k_roi_align_nhwc4d outside its envelope)
+               "mb_multiscale_roi_align": 2,  # k_roi_geom + k_roi_align_tma (k_roi_align_nhwc4d alone outside the envelope)
                "mb_det_postprocess": 7,       # k_det_init, k_det_candidates, k_seg_meta, k_rank_in_segment, k_nms_mask, k_nms_sweep_small, k_det_finalize
                "mb_crop_plan": 1, "mb_crop_gather": 1}
 
@@ -167,7 +167,7 @@ class HotPath:
         nb = self.lib.mb_roi_align_workspace_bytes(C.byref(self.roi_params), self.s.num_images * self.R)
         self.roi_ws = torch.empty((nb,), dtype=torch.uint8, device=self.dev) if nb else None
         self.features_layout = "channels_last" if nhwc else "nchw"
-        self.kernel_launches_per_step = sum(self.KERNELS.values()) + (len(features) if nb else 0)   # + k_nchw_to_nhwc per level
+        self.kernel_launches_per_step = sum(self.KERNELS.values()) + (len(features) if (nb and not nhwc) else 0)   # + k_nchw_to_nhwc per level
         for i, im in enumerate(images):
             self.crop_params.images[i] = im.data_ptr()
         self.class_logits, self.box_regression = class_logits, box_regression

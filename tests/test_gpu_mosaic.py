@@ -33,7 +33,7 @@ def make_plan(w, rank, world, batch=4):
         return pipeline.HotPath(w.shapes(n), w.base.rpn, w.base.det, threshold=w.base.threshold, crop_capacity_bytes=1 << 20, device=DEV)
 
     plan = mosaic.MosaicPlan(grid, w.tile, (w.height, w.width), make_hp, sizes, rank=rank, world=world,
-                             threshold=w.base.threshold, iou_threshold=w.base.det.nms_thresh, crop_capacity_bytes=64 << 20, device=DEV)
+                             threshold=w.base.threshold, iou_threshold=w.base.det.nms_thresh, crop_capacity_bytes=256 << 20, device=DEV)
     batches, i0 = [], 0
     for n in sizes:
         batches.append(w.batch_inputs(mine[i0:i0 + n], DEV))

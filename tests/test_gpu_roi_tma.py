@@ -55,9 +55,13 @@ def test_tma_equals_gather_and_oracle_single_level(ops, channels):
     x = rng.standard_normal((n, channels, h, w)).astype(F)
     rois = mixed_rois(rng, n, 600, (h * 4, w * 4))
     xc = cu(x).contiguous(memory_format=torch.channels_last)
+    lib = ops._lib.load()
     for exact in (True, False):
+        n0 = lib.mb_roi_align_tma_launches()
         a = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact)
+        assert lib.mb_roi_align_tma_launches() == n0 + 1          # the TMA-staged kernel produced `a`
         b = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather=True)
+        assert lib.mb_roi_align_tma_launches() == n0 + 1          # ... and the gather kernel `b`
         if exact:
             assert torch.equal(a, b)
         else:
@@ -129,7 +133,10 @@ def test_tma_per_image_layout_with_dead_rows(ops):
             p.level_thresholds[i] = t
         p.boxes_per_image, p.box_counts = R, tc.data_ptr()
         out = torch.full((n * R, c, 7, 7), 7.0, device=DEV)
-        _lib.check(_lib.load().mb_multiscale_roi_align(C.byref(p), _ptr(tb), n * R, _ptr(out), None, None, 0, _stream(tb)), "roi")
+        nb = _lib.load().mb_roi_align_workspace_bytes(C.byref(p), n * R)
+        assert nb > 0
+        ws = torch.empty((nb,), dtype=torch.uint8, device=DEV)
+        _lib.check(_lib.load().mb_multiscale_roi_align(C.byref(p), _ptr(tb), n * R, _ptr(out), None, _ptr(ws), nb, _stream(tb)), "roi")
         outs.append(out)
     assert torch.equal(outs[0], outs[1])
     o = outs[0].cpu().numpy().reshape(n, R, c, 7, 7)

@@ -78,7 +78,7 @@ def test_mosaic_plan_world1_matches_the_cpu_composition():
     keep = R.seam_keep_rows(block, w.base.det.nms_thresh)
     state = plan.seam.state.cpu().numpy()
     assert np.array_equal(np.nonzero(state == 1)[0], keep)
-    assert 0 < len(keep) < int((block[:, 5] >= 0).sum())
+    assert 0 < len(keep) <= int((block[:, 5] >= 0).sum())      # independent random tiles: (almost) nothing to suppress; duplicates are tests/test_gpu_seam.py's job
     mosaic_px = w.band(0, w.height, DEV).cpu().numpy()
     xywh, ci, crops = R.crops_of_rows(mosaic_px, block, keep)
     assert res["count"] == len(keep) and np.array_equal(res["src"].cpu().numpy(), keep)

@@ -285,6 +285,7 @@ class MosaicPlan:
         self.hooks = {}
         self.launches_per_run = 0
         self._tile_launches = 0
+        self._use = {n: 0 for n in self.slots}
 
     def bind_band(self, band_u8: Tensor, band_y0: int) -> None:
         self.crops.bind_band(band_u8, band_y0)
@@ -293,9 +294,9 @@ class MosaicPlan:
     def _c(s) -> C.c_void_p:
         return C.c_void_p(s.cuda_stream)
 
-    def run(self, batches: Sequence[Dict[str, Sequence[Tensor]]]) -> None:
+    def run(self, batches, serial: bool = False) -> None:
         """Enqueue one whole mosaic pass of this rank (no host sync). Results: self.seam.state, self.crops.*"""
-        self.run_tiles(batches)
+        self.run_tiles(batches, serial=serial)
         if self.world > 1:
             exchange(self.block, self.world, self.group, out=self.gathered)
         self.run_tail()
@@ -309,46 +310,133 @@ class MosaicPlan:
         self.crops.launch(self.gathered, self.seam.state, self.rank * self.block_rows)
         self.launches_per_run = self._tile_launches + 6 + 3      # seam: prep, pairs, 3 rounds, finish; select, plan, gather
 
-    def run_tiles(self, batches: Sequence[Dict[str, Sequence[Tensor]]]) -> None:
-        """This rank's tiles through rpn | roi_align | detections (three batches in flight) into self.block."""
+    def run_tiles(self, batches, serial: bool = False, first: int = 0, count: Optional[int] = None) -> None:
+        """This rank's tiles through rpn | roi_align | detections into self.block. `batches`: sequence of per-batch
+        input dicts, or a callable (batch_index, n_tiles, stream) -> dict invoked right before the batch is enqueued
+        (the host-fed pipeline copies the inputs in and makes `stream` wait for them there). Three batches are in
+        flight on three streams unless `serial` (everything on the current stream, one kernel at a time: the mode
+        whose per-kernel timings are those of the kernel running alone). `first`/`count` select a run of batches."""
         cur = torch.cuda.current_stream(self.dev)
-        for s in (self.sR, self.sA, self.sD):
-            s.wait_stream(cur)
-        t0 = 0
-        use = {n: 0 for n in self.slots}
-        launches = 0
-        for bi, (n, inp) in enumerate(zip(self.batch_sizes, batches)):
-            i = use[n] % len(self.slots[n])
-            use[n] += 1
+        sR, sA, sD = (cur, cur, cur) if serial else (self.sR, self.sA, self.sD)
+        if not serial:
+            for s in (sR, sA, sD):
+                s.wait_stream(cur)
+        last = len(self.batch_sizes) if count is None else first + count
+        t0 = sum(self.batch_sizes[:first])
+        if first == 0:
+            self._use = {n: 0 for n in self.slots}
+            self._tile_launches = 0
+        hooks = self.hooks
+        for bi in range(first, last):
+            n = self.batch_sizes[bi]
+            i = self._use[n] % len(self.slots[n])
+            self._use[n] += 1
             hp, ev = self.slots[n][i], self.ev[n][i]
-            if self.used[n][i]:
-                self.sR.wait_event(ev["done"])               # the slot's proposals / detections are free again
+            if self.used[n][i] and not serial:
+                sR.wait_event(ev["done"])                    # the slot's proposals / detections are free again
             self.used[n][i] = True
+            inp = batches(bi, n, sR) if callable(batches) else batches[bi - first if count is not None else bi]
             hp.rebind(inp["objectness"], inp["deltas"], inp["features"], inp["class_logits"], inp["box_regression"])
-            hp.rpn(self._c(self.sR))
-            ev["rpn"].record(self.sR)
-            self.sA.wait_event(ev["rpn"])
-            if "before_roi" in self.hooks:
-                self.hooks["before_roi"](self.sA)
-            hp.roi_align(self._c(self.sA))
-            if "after_roi" in self.hooks:
-                self.hooks["after_roi"](self.sA)
-            ev["roi"].record(self.sA)
-            self.sD.wait_event(ev["roi"])
-            hp.detections(self._c(self.sD))
+            hp.rpn(self._c(sR))
+            if not serial:
+                ev["rpn"].record(sR)
+                sA.wait_event(ev["rpn"])
+            if "before_roi" in hooks:
+                hooks["before_roi"](bi, hp, sA)
+            hp.roi_align(self._c(sA))
+            if "after_roi" in hooks:
+                hooks["after_roi"](bi, hp, sA)
+            if not serial:
+                ev["roi"].record(sA)
+                sD.wait_event(ev["roi"])
+            hp.detections(self._c(sD))
             _lib.check(self.lib.mb_mosaic_pack(_p(hp.det_boxes), _p(hp.det_scores), _p(hp.det_labels), _p(hp.det_counts),
                                                C.c_void_p(self.origins.data_ptr() + t0 * 8), n, self.dpi, self.threshold,
                                                n * self.dpi, C.c_void_p(self.block.data_ptr() + t0 * self.dpi * 24),
-                                               self._c(self.sD)), "mb_mosaic_pack")
-            ev["done"].record(self.sD)
-            launches += hp.kernel_launches_per_step - 2 + 1      # no per-batch crop stage; + pack
+                                               self._c(sD)), "mb_mosaic_pack")
+            if not serial:
+                ev["done"].record(sD)
+            if "batch_done" in hooks:
+                hooks["batch_done"](bi, hp, sD)
+            self._tile_launches += hp.kernel_launches_per_step - 2 + 1      # no per-batch crop stage; + k_mosaic_pack
             t0 += n
-        cur.wait_stream(self.sD)
-        self._tile_launches = launches
+        if not serial:
+            cur.wait_stream(sD)
 
     def results(self) -> Dict[str, Tensor]:
         self.seam.check()
         return self.crops.results()
+
+
+class HostMosaicRunner:
+    """Host-facing driver of a MosaicPlan: every batch's head outputs arrive in (pinned) host memory and are copied
+    to the device on a copy-in stream while earlier batches compute; the rank's results (annotation bounds, crop
+    rectangles, crop bytes) are read back into pinned host memory. `depth` device input slots per batch size."""
+
+    def __init__(self, plan: MosaicPlan, examples: Dict[int, Dict[str, Sequence[Tensor]]], depth: int = 4):
+        self.plan, self.dev, self.depth = plan, plan.dev, int(depth)
+        self.s_in = torch.cuda.Stream(device=self.dev)
+        self.s_out = torch.cuda.Stream(device=self.dev)
+        self.slots = {n: [{k: [torch.empty_like(t, device=self.dev) for t in v] for k, v in ex.items()} for _ in range(self.depth)]
+                      for n, ex in examples.items()}
+        self.ev_in = {n: [torch.cuda.Event() for _ in range(self.depth)] for n in examples}
+        self.ev_free = {n: [None] * self.depth for n in examples}
+        c = plan.crops
+        self.small = {k: torch.empty_like(getattr(c, k), device="cpu").pin_memory() for k in ("rects", "xywh", "src", "offsets", "totals")}
+        self.pix = torch.empty((c.capacity,), dtype=torch.uint8).pin_memory()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def run(self, host_batches: Sequence[Dict[str, Sequence[Tensor]]]):
+        plan = self.plan
+        use = {n: 0 for n in self.slots}
+        cur_slot = {}
+        self.h2d_bytes = 0
+
+        def feed(bi, n, stream):
+            i = use[n] % self.depth
+            use[n] += 1
+            cur_slot[bi] = (n, i)
+            if self.ev_free[n][i] is not None:
+                self.s_in.wait_event(self.ev_free[n][i])          # the batch that last used this slot has been consumed
+            dst = self.slots[n][i]
+            with torch.cuda.stream(self.s_in):
+                for k, hs in host_batches[bi].items():
+                    for src, d in zip(hs, dst[k]):
+                        d.copy_(src, non_blocking=True)
+                        self.h2d_bytes += src.numel() * src.element_size()
+                self.ev_in[n][i].record(self.s_in)
+            stream.wait_event(self.ev_in[n][i])
+            return dst
+
+        def done(bi, hp, stream):
+            n, i = cur_slot[bi]
+            if self.ev_free[n][i] is None:
+                self.ev_free[n][i] = torch.cuda.Event()
+            self.ev_free[n][i].record(stream)
+
+        plan.hooks["batch_done"] = done
+        try:
+            plan.run(feed)
+        finally:
+            plan.hooks.pop("batch_done", None)
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_out.wait_stream(cur)
+        c = plan.crops
+        with torch.cuda.stream(self.s_out):
+            for k, h in self.small.items():
+                h.copy_(getattr(c, k), non_blocking=True)
+        self.s_out.synchronize()
+        tot = self.small["totals"].tolist()
+        if tot[2]:
+            raise MisoB200Error(f"mosaic crop buffer too small: {tot[1]} bytes needed")
+        with torch.cuda.stream(self.s_out):
+            self.pix[:tot[1]].copy_(c.pixels[:tot[1]], non_blocking=True)
+        self.s_out.synchronize()
+        self.d2h_bytes = sum(h.numel() * h.element_size() for h in self.small.values()) + tot[1]
+        k = tot[0]
+        return {"count": k, "bytes": tot[1], "rects": self.small["rects"][:k], "xywh": self.small["xywh"][:k],
+                "src": self.small["src"][:k], "offsets": self.small["offsets"][:k + 1], "pixels": self.pix[:tot[1]]}
 
 
 def by_score(gathered: Tensor, state: Tensor) -> Tensor:

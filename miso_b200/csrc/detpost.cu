@@ -45,6 +45,8 @@ struct DetScratch {
     float* seg_offset;          // [G]
     unsigned long long* keepbits;
     unsigned long long* mask;
+    unsigned long long* gkeys;  // [N * gcap] sort scratch in global memory, only when the per-image bound exceeds shared memory
+    int gcap;
     SegArrays seg;
     size_t zero_bytes;
     long long mask_words;
@@ -69,6 +71,10 @@ static void carve_det(Carver& c, DetScratch& w, const DetDev& d) {
     w.keepbits = c.take<unsigned long long>((size_t)G * (d.max_props / 64 + 2));
     w.mask_words = (long long)G * d.max_props * ((d.max_props + 63) / 64);
     w.mask = c.take<unsigned long long>((size_t)w.mask_words);
+    const long long per_seg = d.max_props < d.dpi ? d.max_props : d.dpi;
+    const long long bound = (long long)(d.C - 1) * per_seg;
+    w.gcap = bound > kDetSortCap ? next_pow2((int)bound) : 0;
+    w.gkeys = w.gcap ? c.take<unsigned long long>((size_t)d.N * w.gcap) : nullptr;
 }
 
 __global__ void __launch_bounds__(kDetThreads) k_det_candidates(const DetDev d, const DetImages im,
@@ -117,20 +123,34 @@ __global__ void __launch_bounds__(kDetThreads) k_det_candidates(const DetDev d, 
 }
 
 // one launch for the per-call initialisation: clear the counters region, mark every bucket slot as a hole (-1)
-// and write the fixed segment starts (instead of two memsets and a kernel)
-__global__ void __launch_bounds__(256) k_det_init(int G, int max_props, int* __restrict__ seg_start, uint4* __restrict__ zero16,
+// and write the fixed segment starts (instead of two memsets and a kernel). seg_start lies INSIDE the cleared
+// region: the thread that clears a 16-byte vector overlapping it writes the final values instead of zeros, so no
+// word is written by two threads (no ordering between threads is assumed).
+__global__ void __launch_bounds__(256) k_det_init(int G, int max_props, long long seg_start_vec, uint4* __restrict__ zero16,
                                                   long long zero_vecs, int* __restrict__ bseg, long long P) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-    for (long long j = i; j < zero_vecs; j += stride) zero16[j] = make_uint4(0u, 0u, 0u, 0u);
+    const long long seg_vecs = ((long long)G + 3) / 4;
+    for (long long j = i; j < zero_vecs; j += stride) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        const long long s = j - seg_start_vec;
+        if (s >= 0 && s < seg_vecs) {
+            const long long g0 = 4 * s;
+            v.x = g0 < G ? (unsigned)(g0 * max_props) : 0u;
+            v.y = g0 + 1 < G ? (unsigned)((g0 + 1) * max_props) : 0u;
+            v.z = g0 + 2 < G ? (unsigned)((g0 + 2) * max_props) : 0u;
+            v.w = g0 + 3 < G ? (unsigned)((g0 + 3) * max_props) : 0u;
+        }
+        zero16[j] = v;
+    }
     for (long long j = i; j < P; j += stride) bseg[j] = -1;
-    if (i < G) seg_start[i] = (int)i * max_props;
 }
 
 __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev d, const DetImages im, DetScratch w,
                                                                   float4* det_boxes, float4* det_boxes_net,
                                                                   float* det_scores, long long* det_labels,
-                                                                  int* det_counts, int use_merge) {
-    extern __shared__ unsigned long long keys[];
+                                                                  int* det_counts, int use_merge, int smem_keys) {
+    extern __shared__ unsigned long long keys_smem[];
+    unsigned long long* keys = keys_smem;
     __shared__ int s_cnt;
     __shared__ int run_off[kDetMergeMaxRuns + 1];
     __shared__ int wpre[kDetMergeMaxRuns][kSweepSmallMaxWords + 1];
@@ -181,6 +201,22 @@ __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev 
     } else {
         if (tid == 0) s_cnt = 0;
         __syncthreads();
+        if (w.gcap) {
+            // many classes (e.g. the 91-class COCO head at 300 detections): the worst case does not fit shared memory.
+            // Count what was actually kept; only if THAT exceeds the shared buffer is the sort done in global memory.
+            int local = 0;
+            for (int c = 0; c < S; ++c) {
+                const int g = n * S + c;
+                const unsigned long long* kb = w.keepbits + w.seg.keep_off[g];
+                for (int q = tid; q < w.seg.seg_words[g]; q += kDetFinalThreads) local += __popcll(kb[q]);
+            }
+            if (local) atomicAdd(&s_cnt, local);
+            __syncthreads();
+            if (next_pow2(max(s_cnt, 2)) > smem_keys) keys = w.gkeys + (size_t)n * w.gcap;
+            __syncthreads();
+            if (tid == 0) s_cnt = 0;
+            __syncthreads();
+        }
         for (int c = 0; c < S; ++c) {
             const int g = n * S + c;
             const int cnt = w.seg.seg_count[g], st = w.seg.seg_start[g];
@@ -226,7 +262,7 @@ static int make_det(const mb_det_params& p, DetDev& d, DetImages& im) {
     d.score_thresh = p.score_thresh; d.min_size = p.min_size;
     d.dw = DecodeWeights{p.wx, p.wy, p.ww, p.wh, p.bbox_xform_clip};
     const long long per_seg = d.max_props < d.dpi ? d.max_props : d.dpi;
-    if ((long long)(d.C - 1) * per_seg > kDetSortCap) return MB_ERR_UNSUPPORTED;
+    if ((long long)(d.C - 1) * per_seg >= (1ll << 24)) return MB_ERR_UNSUPPORTED;
     if ((long long)d.N * (d.C - 1) * d.max_props >= (1ll << 30)) return MB_ERR_UNSUPPORTED;
     for (int n = 0; n < d.N; ++n) {
         im.h[n] = p.image_h[n]; im.w[n] = p.image_w[n];
@@ -269,7 +305,9 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     if (!c.ok()) return MB_ERR_WORKSPACE;
     const int G = d.N * (d.C - 1);
     if ((w.zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MB_ERR_INVALID_ARG;
-    k_det_init<<<max(ceil_div(G, 256), 32), 256, 0, stream>>>(G, d.max_props, w.seg.seg_start, (uint4*)workspace,
+    const size_t seg_start_off = (size_t)((const char*)w.seg.seg_start - (const char*)workspace);
+    if ((seg_start_off & 15) != 0 || seg_start_off + 4 * (size_t)((G + 3) / 4 * 4) > w.zero_bytes) return MB_ERR_INVALID_ARG;
+    k_det_init<<<max(ceil_div(G, 256), 32), 256, 0, stream>>>(G, d.max_props, (long long)(seg_start_off / 16), (uint4*)workspace,
                                                               (long long)(w.zero_bytes / 16), w.bseg, (long long)w.P);
     MB_LAUNCH_CHECK();
     k_det_candidates<<<ceil_div(d.N * d.max_props, kDetThreads), kDetThreads, 0, stream>>>(
@@ -286,11 +324,12 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     const long long per_seg = d.max_props < d.dpi ? d.max_props : d.dpi;
     const int bound = (int)((d.C - 1) * per_seg);
     const int use_merge = (d.C - 1) <= kDetMergeMaxRuns && d.max_props <= 64 * kSweepSmallMaxWords && 2 * bound <= kDetSortCap;
-    const int cap = use_merge ? 2 * bound : next_pow2(bound > 2 ? bound : 2);   // merge keeps source + merged order
+    int cap = use_merge ? 2 * bound : next_pow2(bound > 2 ? bound : 2);   // merge keeps source + merged order
+    if (cap > kDetSortCap) cap = kDetSortCap;                             // larger actual counts sort in w.gkeys
     const int smem = (cap > 2 ? cap : 2) * (int)sizeof(unsigned long long);
     MB_CUDA(cudaFuncSetAttribute(k_det_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k_det_finalize<<<d.N, kDetFinalThreads, smem, stream>>>(d, im, w, (float4*)det_boxes, (float4*)det_boxes_net, det_scores,
-                                                           (long long*)det_labels, det_counts, use_merge);
+                                                           (long long*)det_labels, det_counts, use_merge, cap);
     MB_LAUNCH_CHECK();
     return MB_OK;
 }

@@ -124,7 +124,10 @@ def test_det_postprocess_matches_golden(det, golden_dir):
         assert np.max(np.abs(scores[i].cpu().numpy() - g[f"scores{i}"])) < 1e-6
 
 
-@pytest.mark.parametrize("ncls,props,dpi,rule", [(3, 1000, 300, 4000), (3, 1000, 300, -1), (11, 400, 100, 4000), (2, 50, 100, 100000)])
+# (91, 1000, 300): the stock COCO head at miso's box_detections_per_img=300 (ref:miso/object_detection/models.py:9) — 90 x 300
+# candidate slots per image exceed the shared-memory sort; the kernel counts what was kept and sorts in global memory if needed
+@pytest.mark.parametrize("ncls,props,dpi,rule", [(3, 1000, 300, 4000), (3, 1000, 300, -1), (11, 400, 100, 4000), (2, 50, 100, 100000),
+                                                  (91, 1000, 300, 4000)])
 def test_det_postprocess_matches_oracle(det, ncls, props, dpi, rule):
     logits, reg, proposals, shapes = cases.det_case(n_img=3, props=props, num_classes=ncls, seed=5 + ncls)
     n = len(proposals)
@@ -153,6 +156,32 @@ def test_det_postprocess_matches_oracle(det, ncls, props, dpi, rule):
     for i in range(n):
         assert np.array_equal(labels[i].cpu().numpy(), ref[i][2])
         assert cases.box_rel_err(boxes[i].cpu().numpy(), ref[i][0]) < 1e-5      # no original size: boxes == boxes_net
+        assert np.max(np.abs(scores[i].cpu().numpy() - ref[i][1])) < 1e-6
+
+
+def test_det_postprocess_many_classes_global_sort_path(det):
+    """91 classes, score threshold 0: every (proposal, class) pair is a candidate, each class keeps up to 300 boxes, so
+    far more than 16384 keys per image reach the final ordering — the global-memory sort path. Vanilla strategy on both sides."""
+    ncls, props, dpi = 91, 600, 300
+    logits, reg, proposals, shapes = cases.det_case(n_img=2, props=props, num_classes=ncls, image_hw=(512, 640), seed=77)
+    n, r = len(proposals), props
+    padded = np.zeros((n, r, 4), np.float32)
+    for i, p in enumerate(proposals):
+        padded[i, :len(p)] = p
+    counts = torch.tensor([len(p) for p in proposals], dtype=torch.int32, device=DEV)
+    cfg = det.DetConfig(detections_per_img=dpi, trick_numel=-1, score_thresh=0.0)
+    out = det.postprocess_detections(cu(logits), cu(reg), cu(padded), counts, shapes, cfg, packed=True)
+    orig = D.batched_nms
+    D.batched_nms = lambda b, s, idx, thr, device_rule="cpu": D.batched_nms_vanilla(b, s, idx, thr)
+    try:
+        ref = D.postprocess_detections(logits, reg, proposals, shapes, score_thresh=0.0, detections_per_img=dpi)
+    finally:
+        D.batched_nms = orig
+    boxes, scores, labels = out.as_lists()
+    for i in range(n):
+        assert len(ref[i][2]) == dpi
+        assert np.array_equal(labels[i].cpu().numpy(), ref[i][2])
+        assert cases.box_rel_err(boxes[i].cpu().numpy(), ref[i][0]) < 1e-5
         assert np.max(np.abs(scores[i].cpu().numpy() - ref[i][1])) < 1e-6
 
 
@@ -200,30 +229,26 @@ def test_crop_full_size_roundtrip(det):
         assert arr.shape == r.shape and np.array_equal(arr, r)
 
 
-def test_seam_nms_sync_free_equals_compacting_version(det):
-    """mosaic.SeamNms (padding rows ignored on the device, no host sync before finish) must give
-    exactly the result of the compacting seam_nms and of the oracle's per-class NMS."""
+def test_dense_seam_nms_and_pack_match_the_cpu_restatement(det):
+    """mb_mosaic_pack == tests/mosaic_ref.pack_block bit for bit; mosaic.SeamNms (dense per-label mb_nms, padding rows
+    ignored on the device, no host sync before finish) == the oracle's per-class NMS over the live rows."""
     from miso_b200 import mosaic
+    from tests import mosaic_ref as R
     from tests.test_mosaic_cpu import synth_tiles
     b, s, l, c, o = synth_tiles(num_tiles=6, dpi=60, seed=3)
     block = mosaic.pack_block(cu(b), cu(s), cu(l), cu(c).to(torch.int32), cu(o), 0.5, 6 * 60 + 17)
-    # mb_mosaic_pack (one launch) == the tensor-operation formulation used by the CPU/gloo host-logic tests
-    host_block = mosaic.pack_block(torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(l),
-                                   torch.from_numpy(c).to(torch.int32), torch.from_numpy(o), 0.5, 6 * 60 + 17)
-    assert torch.equal(block.cpu(), host_block)
-    ref_b, ref_s, ref_l = mosaic.seam_nms(block, 0.5)
+    host_block = R.pack_block(b, s, l, c, o, 0.5, 6 * 60 + 17)
+    assert np.array_equal(block.cpu().numpy(), host_block)
     seam = mosaic.SeamNms(block.shape[0], 3, DEV)
     seam.launch(block, 0.5)
-    gb, gs, gl = seam.finish()
-    assert torch.equal(gb, ref_b) and torch.equal(gs, ref_s) and torch.equal(gl, ref_l)
-    live = block[:, 5] >= 0
-    rows = block[live].cpu().numpy()
-    keep = D.batched_nms_vanilla(rows[:, :4], rows[:, 4], rows[:, 5].astype(np.int64), 0.5)
-    assert np.array_equal(gb.cpu().numpy(), rows[keep, :4])
-    # idempotent and reusable
-    seam.launch(block, 0.5)
-    gb2, _, _ = seam.finish()
-    assert torch.equal(gb2, gb)
+    gb, gs, gl, rows = seam.finish()
+    live = np.nonzero(host_block[:, 5] >= 0)[0]
+    keep = D.batched_nms_vanilla(host_block[live, :4], host_block[live, 4], host_block[live, 5].astype(np.int64), 0.5)
+    assert np.array_equal(rows.cpu().numpy(), live[keep])            # batched_nms order: score desc, row asc
+    assert np.array_equal(gb.cpu().numpy(), host_block[live[keep], :4])
+    assert np.array_equal(np.sort(rows.cpu().numpy()), R.seam_keep_rows(host_block, 0.5))
+    seam.launch(block, 0.5)                                          # idempotent and reusable
+    assert torch.equal(seam.finish()[3], rows)
 
 
 def test_filter_and_crop_many_slots_multi_round(det):

@@ -67,21 +67,27 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~20 us pass. Without
+// the hint the instruction returned after ~300 cycles and the polling loops of 16 single lanes ate 30 % of the SM's
+// issue slots (ncu: 60 M of 197 M executed instructions).
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
-// A wait that cannot hang the GPU: a barrier that never completes (a protocol bug) traps after ~seconds.
+// A wait that cannot hang the GPU: a barrier that never completes (a protocol bug) traps after seconds.
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 20)) __trap();
     }
+}
+__device__ __forceinline__ void st_shared(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 // Warp-level wait: one lane polls, __syncwarp() releases the others. An mbarrier operation issued by all 32 lanes
 // costs ~32 cycles of the SM's shared-memory atomic path (measured: with every lane of 14 consumer warps polling,
@@ -452,111 +458,121 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
     } else {
         // =========================== consumers ===========================
         const int halves = (C + 127) >> 7;
-        const int T = PW * halves;                    // tasks per pooled row
+        const int T = PW * halves;                    // tasks per pooled row; task t = (half t / PW, pooled column t % PW)
+        const bool one_task = T <= kTmaConsumers;     // detection box head: 7 columns x 2 halves = one task per warp and pooled row
+        const int first_half = warp / PW, first_pw = warp - first_half * PW;
         const int rot4 = lane >> 3;
-        int so4[4];
+        unsigned so4[4];                              // byte offsets of the rotated channel rows in the output buffer
 #pragma unroll
-        for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * nbins;
+        for (int t = 0; t < 4; ++t) so4[t] = (unsigned)(((rot4 + t) & 3) * nbins) * 4u;
+        const unsigned ring_lane = s_base + L.ring + lane * 16;
         int seq0 = 0;                                 // sequence number of the current RoI's first staged row
+        // per-task state of the pooled column: tap column offsets (+ the channel half), weights, pattern, output column
+        unsigned co[4];
+        float2 wx[4];
+        int px = 0, xv = 0, c0 = 0;
+        unsigned ocol = 0;
         for (int it = 0; it < my_rois; ++it) {
             const int gs = it % kGeomSlots, b = it & 1, u = it >> 1;
             mbar_wait_warp(b_gfull + 8 * gs, (it / kGeomSlots) & 1, lane);
             const TmaGeom& G = geom[gs];
             const int mode = G.mode, nrows = G.nrows;
             if (u >= 1) mbar_wait_warp(b_ofree + 8 * b, (u - 1) & 1, lane);
-            float* ob = reinterpret_cast<float*>(smem_raw + L.ob + b * ob_bytes);
+            const unsigned ob_u32 = s_base + L.ob + b * ob_bytes;
+            auto load_x = [&](int pw, int half) {
+                const uint4 xo = G.xoff[pw];
+                const float4 xa = G.xwa[pw], xb = G.xwb[pw];
+                const unsigned hoff = (unsigned)half * 512u;
+                co[0] = xo.x + hoff; co[1] = xo.y + hoff; co[2] = xo.z + hoff; co[3] = xo.w + hoff;
+                wx[0] = make_float2(xa.x, xa.y); wx[1] = make_float2(xa.z, xa.w);
+                wx[2] = make_float2(xb.x, xb.y); wx[3] = make_float2(xb.z, xb.w);
+                const int xi = G.xinfo[pw];
+                px = xi & 3; xv = (xi >> 2) & 3;
+                c0 = half * 128 + 4 * lane;
+                ocol = ob_u32 + (unsigned)(c0 * nbins + pw) * 4u;
+            };
             if (mode == 0) {
-                float4* o4 = reinterpret_cast<float4*>(ob);
+                float4* o4 = reinterpret_cast<float4*>(smem_raw + L.ob + b * ob_bytes);
                 for (unsigned i = warp * 32 + lane; i < ob_bytes / 16; i += kTmaConsumers * 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
                 int waited = 0, released = 0;
-                const char* gimg = reinterpret_cast<const char*>(G.img);
-                float2 wx[4];
-                unsigned co[4];
-                int xi = 0, cur_pw = -1;
+                const char* gimg = reinterpret_cast<const char*>(G.img) + lane * 16;
+                if (one_task && warp < T) load_x(first_pw, first_half);
                 for (int ph = 0; ph < PH; ++ph) {
                     const int yi = G.yinfo[ph];
                     const int need = (yi >> 8) & 0xff, rel = (yi >> 16) & 0xff;
-                    if (mode == 1) {
-                        if (waited < need) {
-                            if (lane == 0)
-                                for (int q = waited; q < need; ++q) {
-                                    const int s = seq0 + q;
-                                    mbar_wait(b_full + 8 * (s & (kRowSlots - 1)), (s >> 6) & 1);
-                                }
-                            __syncwarp();
-                            waited = need;
-                        }
-                    }
-                    const int4 yx = G.yidx[ph];
-                    const float4 ya = G.ywa[ph], yb = G.ywb[ph];
-                    const float2 wy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y),
-                                          make_float2(yb.z, yb.w)};
-                    const int py = yi & 3, yv = (yi >> 2) & 3;
-                    unsigned rs[4];
-                    const char* rg[4];
-                    if (mode == 1) {
-                        const unsigned lb = s_base + L.ring + lane * 16;
-                        const bool a_ok = (yv & 1) != 0, b_ok = (yv & 2) != 0;
-                        // slots of invalid samples are never read; give them the address of slot 0 of the ring
-                        rs[0] = lb + (a_ok ? (unsigned)rowoff[(seq0 + yx.x) & (kRowSlots - 1)] : 0u);
-                        rs[1] = lb + (a_ok ? (unsigned)rowoff[(seq0 + yx.y) & (kRowSlots - 1)] : 0u);
-                        rs[2] = lb + (b_ok ? (unsigned)rowoff[(seq0 + yx.z) & (kRowSlots - 1)] : 0u);
-                        rs[3] = lb + (b_ok ? (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)] : 0u);
-                    } else {
-                        rg[0] = gimg + (unsigned)yx.x + lane * 16;
-                        rg[1] = gimg + (unsigned)yx.y + lane * 16;
-                        rg[2] = gimg + (unsigned)yx.z + lane * 16;
-                        rg[3] = gimg + (unsigned)yx.w + lane * 16;
-                    }
-                    for (int t = warp; t < ((dbg & 2) ? 0 : T); t += kTmaConsumers) {      // probe bit 1: no arithmetic
-                        const int half = t / PW, pw = t - half * PW;
-                        if (pw != cur_pw) {
-                            cur_pw = pw;
-                            const uint4 xo = G.xoff[pw];
-                            const float4 xa = G.xwa[pw], xb = G.xwb[pw];
-                            co[0] = xo.x; co[1] = xo.y; co[2] = xo.z; co[3] = xo.w;
-                            wx[0] = make_float2(xa.x, xa.y); wx[1] = make_float2(xa.z, xa.w);
-                            wx[2] = make_float2(xb.x, xb.y); wx[3] = make_float2(xb.z, xb.w);
-                            xi = G.xinfo[pw];
-                        }
-                        const int c0 = half * 128 + 4 * lane;
-                        if (c0 < C) {
-                            const int px = xi & 3, xv = (xi >> 2) & 3;
-                            const unsigned hoff = (unsigned)half * 512u;
-                            float4 av;
-                            if (mode == 1) {
-                                const unsigned rr[4] = {rs[0] + hoff, rs[1] + hoff, rs[2] + hoff, rs[3] + hoff};
-                                if (yv == 3 && xv == 3) {
-                                    switch (py * 3 + px) {      // warp-uniform
-                                        case 0: av = bin_fast<EXACT, 0, 0>(rr, co, wy, wx, ones); break;
-                                        case 1: av = bin_fast<EXACT, 0, 1>(rr, co, wy, wx, ones); break;
-                                        case 2: av = bin_fast<EXACT, 0, 2>(rr, co, wy, wx, ones); break;
-                                        case 3: av = bin_fast<EXACT, 1, 0>(rr, co, wy, wx, ones); break;
-                                        case 4: av = bin_fast<EXACT, 1, 1>(rr, co, wy, wx, ones); break;
-                                        case 5: av = bin_fast<EXACT, 1, 2>(rr, co, wy, wx, ones); break;
-                                        case 6: av = bin_fast<EXACT, 2, 0>(rr, co, wy, wx, ones); break;
-                                        case 7: av = bin_fast<EXACT, 2, 1>(rr, co, wy, wx, ones); break;
-                                        default: av = bin_fast<EXACT, 2, 2>(rr, co, wy, wx, ones); break;
-                                    }
-                                } else {
-                                    av = bin_generic<EXACT>(rr, co, wy, wx, py, px, yv, xv, ones);
-                                }
-                            } else {
-                                const char* rr[4] = {rg[0] + hoff, rg[1] + hoff, rg[2] + hoff, rg[3] + hoff};
-                                av = bin_generic<EXACT>(rr, co, wy, wx, py, px, yv, xv, ones);
+                    if (mode == 1 && waited < need) {
+                        if (lane == 0)
+                            for (int q = waited; q < need; ++q) {
+                                const int s = seq0 + q;
+                                mbar_wait(b_full + 8 * (s & (kRowSlots - 1)), (s >> 6) & 1);
                             }
-                            rotate4(av, rot4);
-                            float* o = ob + (size_t)c0 * nbins + ph * PW + pw;
-                            o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
+                        __syncwarp();
+                        waited = need;
+                    }
+                    if (!(dbg & 2) && warp < T) {                                            // probe bit 1: no arithmetic
+                        const int4 yx = G.yidx[ph];
+                        const float4 ya = G.ywa[ph], yb = G.ywb[ph];
+                        const float2 wy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y),
+                                              make_float2(yb.z, yb.w)};
+                        const int py = yi & 3, yv = (yi >> 2) & 3;
+                        const unsigned orow = (unsigned)(ph * PW) * 4u;
+                        int pw = first_pw, half = first_half;
+                        if (mode == 1) {
+                            // slots of invalid samples are never read (their ordinals are 0: some staged row's offset)
+                            unsigned rs[4];
+                            rs[0] = ring_lane + (unsigned)rowoff[(seq0 + yx.x) & (kRowSlots - 1)];
+                            rs[1] = ring_lane + (unsigned)rowoff[(seq0 + yx.y) & (kRowSlots - 1)];
+                            rs[2] = ring_lane + (unsigned)rowoff[(seq0 + yx.z) & (kRowSlots - 1)];
+                            rs[3] = ring_lane + (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)];
+                            for (int t = warp; t < T; t += kTmaConsumers) {
+                                if (!one_task) load_x(pw, half);
+                                if (c0 < C) {
+                                    float4 av;
+                                    if (yv == 3 && xv == 3) {
+                                        switch (py * 3 + px) {      // warp-uniform
+                                            case 0: av = bin_fast<EXACT, 0, 0>(rs, co, wy, wx, ones); break;
+                                            case 1: av = bin_fast<EXACT, 0, 1>(rs, co, wy, wx, ones); break;
+                                            case 2: av = bin_fast<EXACT, 0, 2>(rs, co, wy, wx, ones); break;
+                                            case 3: av = bin_fast<EXACT, 1, 0>(rs, co, wy, wx, ones); break;
+                                            case 4: av = bin_fast<EXACT, 1, 1>(rs, co, wy, wx, ones); break;
+                                            case 5: av = bin_fast<EXACT, 1, 2>(rs, co, wy, wx, ones); break;
+                                            case 6: av = bin_fast<EXACT, 2, 0>(rs, co, wy, wx, ones); break;
+                                            case 7: av = bin_fast<EXACT, 2, 1>(rs, co, wy, wx, ones); break;
+                                            default: av = bin_fast<EXACT, 2, 2>(rs, co, wy, wx, ones); break;
+                                        }
+                                    } else {
+                                        av = bin_generic<EXACT>(rs, co, wy, wx, py, px, yv, xv, ones);
+                                    }
+                                    rotate4(av, rot4);
+                                    const unsigned o = ocol + orow;
+                                    st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
+                                    st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
+                                }
+                                pw += kTmaConsumers;
+                                while (pw >= PW) { pw -= PW; ++half; }
+                            }
+                        } else {
+                            const char* rg[4] = {gimg + (unsigned)yx.x, gimg + (unsigned)yx.y, gimg + (unsigned)yx.z, gimg + (unsigned)yx.w};
+                            for (int t = warp; t < T; t += kTmaConsumers) {
+                                if (!one_task) load_x(pw, half);
+                                if (c0 < C) {
+                                    float4 av = bin_generic<EXACT>(rg, co, wy, wx, py, px, yv, xv, ones);
+                                    rotate4(av, rot4);
+                                    const unsigned o = ocol + orow;
+                                    st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
+                                    st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
+                                }
+                                pw += kTmaConsumers;
+                                while (pw >= PW) { pw -= PW; ++half; }
+                            }
                         }
                     }
-                    __syncwarp();
-                    if (mode == 1) {
-                        while (released < rel) {
-                            if (lane == 0) mbar_arrive(b_empty + 8 * ((seq0 + released) & (kRowSlots - 1)));
-                            ++released;
-                        }
+                    if (mode == 1 && released < rel) {
+                        __syncwarp();
+                        if (lane == 0)
+                            for (int q = released; q < rel; ++q) mbar_arrive(b_empty + 8 * ((seq0 + q) & (kRowSlots - 1)));
+                        released = rel;
                     }
                 }
                 seq0 += nrows;

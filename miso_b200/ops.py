@@ -338,9 +338,18 @@ def convert_boxes_to_roi_format(boxes: Sequence[Tensor]) -> Tensor:
 
 def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence[float], thresholds: Sequence[float],
                       output_size: Tuple[int, int], sampling_ratio: int, aligned: bool, exact: bool,
-                      return_levels: bool = False, use_workspace: bool = True, force_gather: bool = False):
+                      return_levels: bool = False, use_workspace: bool = True, force_gather: bool = False,
+                      box_counts: Optional[Tensor] = None):
+    """rois: [K, 5] (batch, x1, y1, x2, y2), or — with box_counts [N] int32 — the fused path's [N, R, 4] layout
+    (batch index = row // R, rows beyond an image's count produce zeros; no host sync, no RoI tensor is built)."""
     lib = _lib.load()
     f0 = features[0]
+    per_image = 0
+    if box_counts is not None:
+        torch._assert(rois.dim() == 3 and rois.shape[2] == 4 and rois.shape[0] == f0.shape[0] and
+                      box_counts.dtype == torch.int32 and box_counts.is_contiguous(), "padded RoIs: [N, R, 4] + int32 counts [N]")
+        per_image = int(rois.shape[1])
+        rois = rois.reshape(-1, 4)
     k = rois.shape[0]
     n, c = f0.shape[0], f0.shape[1]
     ph, pw = output_size
@@ -358,6 +367,8 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
                     f.is_contiguous(memory_format=torch.channels_last) for f in features))
         p.channels_last = int(nhwc)
         p.force_gather = int(bool(force_gather))
+        if per_image:
+            p.boxes_per_image, p.box_counts = per_image, box_counts.data_ptr()
         for i, f in enumerate(features):
             torch._assert(f.shape[0] == n and f.shape[1] == c, "all feature maps must share batch and channel sizes")
             fc = f.detach() if nhwc else _f32c(f)
@@ -461,6 +472,12 @@ class MultiScaleRoIAlign(torch.nn.Module):
             _require_cuda(f, "feature map")
         if self.scales is None or self.thresholds is None:
             self._setup(feats, image_shapes)
+        padded = getattr(boxes, "padded", None)
+        if padded is not None and not getattr(boxes, "materialised", True):
+            # the fused RPN stage's [N, R, 4] + counts (patch.LazyProposals): pooled in place, no host sync; the
+            # output has N*R rows (rows beyond an image's count are zero and ignored downstream)
+            return _roi_align_launch(feats, _f32c(padded), self.scales, self.thresholds, self.output_size, self.sampling_ratio,
+                                     False, self.exact, return_levels, force_gather=self.force_gather, box_counts=boxes.counts)
         rois = _f32c(convert_boxes_to_roi_format(boxes))
         return _roi_align_launch(feats, rois, self.scales, self.thresholds, self.output_size, self.sampling_ratio,
                                  False, self.exact, return_levels, force_gather=self.force_gather)

@@ -27,6 +27,35 @@ from .detection import CPU_RULE_NUMEL, CUDA_RULE_NUMEL, DetConfig, RpnConfig
 _RULES = {"cpu": CPU_RULE_NUMEL, "cuda": CUDA_RULE_NUMEL, "vanilla": -1}
 
 
+class LazyProposals(list):
+    """The reference's `list[Tensor]` of per-image proposals, backed by the fused RPN stage's fixed-capacity output
+    ([N, R, 4] + device-side counts). The patched pooler and postprocess_detections read `.padded` / `.counts`
+    directly, so a forward pass never waits for the counts; anything else that indexes or iterates the list
+    materialises the per-image views (one host sync), exactly the reference's structure."""
+
+    def __init__(self, padded: Tensor, counts: Tensor, scores: Optional[Tensor] = None):
+        super().__init__()
+        self.padded, self.counts, self.scores = padded, counts, scores
+        self.materialised = False
+
+    def _fill(self):
+        if not self.materialised:
+            cnt = self.counts.tolist()
+            super().extend(self.padded[i, :c] for i, c in enumerate(cnt))
+            self.materialised = True
+
+    def __len__(self):
+        return int(self.padded.shape[0])
+
+    def __iter__(self):
+        self._fill()
+        return super().__iter__()
+
+    def __getitem__(self, i):
+        self._fill()
+        return super().__getitem__(i)
+
+
 def _rpn_forward(self, images, features: Dict[str, Tensor], targets=None):
     """RegionProposalNetwork.forward (tv:models/detection/rpn.py:336-387), eval branch."""
     if self.training:
@@ -35,24 +64,25 @@ def _rpn_forward(self, images, features: Dict[str, Tensor], targets=None):
     objectness, pred_bbox_deltas = self.head(feats)
     cfg = RpnConfig.from_model(self, trick_numel=self._miso_b200_rule)
     out = detection.rpn_proposals(objectness, pred_bbox_deltas, images.image_sizes, tuple(images.tensors.shape[-2:]), cfg)
-    boxes, _scores = out.as_lists()           # list per image, like the reference (one host sync)
-    return boxes, {}
+    return LazyProposals(out.proposals, out.counts, out.scores), {}     # list per image like the reference, without the sync
 
 
 def _postprocess_detections(self, class_logits: Tensor, box_regression: Tensor, proposals: List[Tensor],
                             image_shapes: List[Tuple[int, int]]):
     """RoIHeads.postprocess_detections (tv:models/detection/roi_heads.py:680-737)."""
-    n = len(proposals)
-    counts = [int(p.shape[0]) for p in proposals]
-    r = max(max(counts), 1)
-    dev = class_logits.device
-    padded = torch.zeros((n, r, 4), dtype=torch.float32, device=dev)
-    for i, p in enumerate(proposals):
-        padded[i, : counts[i]] = p
-    cnt = torch.tensor(counts, dtype=torch.int32, device=dev)
     cfg = DetConfig.from_model(self, trick_numel=self._miso_b200_rule)
-    out = detection.postprocess_detections(class_logits, box_regression, padded, cnt, image_shapes, cfg, packed=True)
-    dc = out.counts.tolist()
+    if isinstance(proposals, LazyProposals) and not proposals.materialised:
+        # logits / regression rows are strided by the proposal capacity (the pooler ran on the padded layout)
+        out = detection.postprocess_detections(class_logits, box_regression, proposals.padded, proposals.counts,
+                                               image_shapes, cfg, packed=False)
+    else:
+        counts = [int(p.shape[0]) for p in proposals]
+        padded = torch.nn.utils.rnn.pad_sequence(list(proposals), batch_first=True)       # [N, max R, 4], one op
+        if padded.shape[1] == 0:
+            padded = torch.zeros((len(counts), 1, 4), dtype=torch.float32, device=class_logits.device)
+        cnt = torch.tensor(counts, dtype=torch.int32, device=class_logits.device)
+        out = detection.postprocess_detections(class_logits, box_regression, padded.contiguous(), cnt, image_shapes, cfg, packed=True)
+    dc = out.counts.tolist()                       # the forward pass's one host sync: the results are variable-length lists
     boxes = [out.boxes_net[i, :c] for i, c in enumerate(dc)]
     scores = [out.scores[i, :c] for i, c in enumerate(dc)]
     labels = [out.labels[i, :c] for i, c in enumerate(dc)]
@@ -63,11 +93,10 @@ def _transform_postprocess(self, result, image_shapes, original_image_sizes):
     """GeneralizedRCNNTransform.postprocess (tv:models/detection/transform.py:257-277)."""
     if self.training:
         return result
+    if not all(pred["boxes"].is_cuda for pred in result):     # decided before anything is resized in place
+        return self._miso_b200_orig_postprocess(result, image_shapes, original_image_sizes)
     for i, (pred, im_s, o_im_s) in enumerate(zip(result, image_shapes, original_image_sizes)):
-        boxes = pred["boxes"]
-        if not boxes.is_cuda:
-            return self._miso_b200_orig_postprocess(result, image_shapes, original_image_sizes)
-        boxes = ops.resize_boxes(boxes, im_s, o_im_s)
+        boxes = ops.resize_boxes(pred["boxes"], im_s, o_im_s)
         result[i]["boxes"] = boxes
         if "masks" in pred:
             result[i]["masks"] = ops.paste_masks_in_image(pred["masks"], boxes, o_im_s)
@@ -94,13 +123,18 @@ def forward_uint8(model, images_u8: List[Tensor]):
     return tr.postprocess(detections, images.image_sizes, original_image_sizes)
 
 
-def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu"):
+def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu", channels_last: bool = True):
     """Swap the post-head stages of a torchvision FasterRCNN / MaskRCNN instance for the CUDA
     path. strategy_rule picks which of torchvision's batched_nms switch-over rules the fused
     stages reproduce: "cpu" (numel > 4000, the reference CPU path = the parity oracle), "cuda"
-    (numel > 100000) or "vanilla" (always per-class). Returns the model."""
+    (numel > 100000) or "vanilla" (always per-class). channels_last moves the backbone + FPN to
+    torch.channels_last: cuDNN then emits the pyramid in NHWC memory, which the RoIAlign kernel gathers in place
+    (an NCHW pyramid costs a transpose of the maps per call). Returns the model."""
     if getattr(model, "_miso_b200_patched", False):
         return model
+    if channels_last:
+        model.backbone.to(memory_format=torch.channels_last)
+    model._miso_b200_channels_last = bool(channels_last)
     rule = _RULES[strategy_rule]
     rpn, heads = model.rpn, model.roi_heads
     rpn._miso_b200_orig_forward = rpn.forward
@@ -132,6 +166,8 @@ def unpatch_model(model):
         h.mask_roi_pool = h._miso_b200_orig_mask_roi_pool
     if hasattr(model.transform, "_miso_b200_orig_postprocess"):
         model.transform.postprocess = model.transform._miso_b200_orig_postprocess
+    if getattr(model, "_miso_b200_channels_last", False):
+        model.backbone.to(memory_format=torch.contiguous_format)
     model._miso_b200_patched = False
     return model
 

@@ -38,12 +38,23 @@ def read_image(path) -> np.ndarray:
     return np.asarray(Image.open(path).convert("RGB"))
 
 
-def _annotate(model, images_meta: List[ImageMetadata], model_labels, threshold, batch_size, project_out: Project):
+def _annotate(model, images_meta: List[ImageMetadata], model_labels, threshold, batch_size, project_out: Project,
+              num_workers: int = 4):
+    """One pass over the images: decode (a pool of `num_workers` threads reads and decodes the next batches while the
+    GPU works — the reference uses a DataLoader with 4 workers, ref:miso/object_detection/inference.py:102-109),
+    patched model, score filter + bounds on the device, annotations."""
+    from concurrent.futures import ThreadPoolExecutor
     from miso_b200 import detection
-    with torch.inference_mode():
-        for i0 in range(0, len(images_meta), batch_size):
+    starts = list(range(0, len(images_meta), batch_size))
+    with torch.inference_mode(), ThreadPoolExecutor(max_workers=max(1, num_workers)) as pool:
+        window = max(2 * batch_size, num_workers)           # images being read / decoded ahead of the GPU
+        futures = [pool.submit(read_image, m.full_path) for m in images_meta[:window]]
+        for bi, i0 in enumerate(starts):
+            arrays = [f.result() for f in futures[i0:i0 + batch_size]]
+            for m in images_meta[len(futures):i0 + batch_size + window]:
+                futures.append(pool.submit(read_image, m.full_path))
+            futures[i0:i0 + batch_size] = [None] * len(arrays)       # release the decoded arrays
             metas = images_meta[i0:i0 + batch_size]
-            arrays = [read_image(m.full_path) for m in metas]
             dev_u8 = [torch.from_numpy(np.ascontiguousarray(a).copy() if not a.flags.writeable else a).cuda() for a in arrays]
             if getattr(model, "_miso_b200_patched", False) and all(a.dim() == 3 and a.shape[2] == 3 for a in dev_u8):
                 from miso_b200.patch import forward_uint8
@@ -51,19 +62,22 @@ def _annotate(model, images_meta: List[ImageMetadata], model_labels, threshold, 
             else:
                 images_cuda = [a.permute(2, 0, 1).to(torch.float32) / 255 for a in dev_u8]       # ToTensor
                 results = model(images_cuda)
-            cap = max(max(int(r["boxes"].shape[0]) for r in results), 1)
-            n = len(results)
-            boxes = torch.zeros((n, cap, 4), dtype=torch.float32, device="cuda")
-            scores = torch.zeros((n, cap), dtype=torch.float32, device="cuda")
-            counts = torch.tensor([int(r["boxes"].shape[0]) for r in results], dtype=torch.int32, device="cuda")
-            for k, r in enumerate(results):
-                boxes[k, : r["boxes"].shape[0]] = r["boxes"]
-                scores[k, : r["scores"].shape[0]] = r["scores"]
-            out = detection.filter_and_crop(dev_u8, boxes, scores, counts, threshold, capacity_bytes=0)
+            pad = torch.nn.utils.rnn.pad_sequence
+            counts_host = [int(r["boxes"].shape[0]) for r in results]
+            boxes = pad([r["boxes"] for r in results], batch_first=True)
+            scores = pad([r["scores"] for r in results], batch_first=True)
+            labels_d = pad([r["labels"] for r in results], batch_first=True)
+            cap = int(boxes.shape[1])
+            if cap == 0:
+                for m in metas:
+                    project_out.add_image(m)
+                continue
+            counts = torch.tensor(counts_host, dtype=torch.int32, device="cuda")
+            out = detection.filter_and_crop(dev_u8, boxes.contiguous(), scores.contiguous(), counts, threshold, capacity_bytes=0)
             kept = int(out.totals[0])
             xywh = out.xywh[:kept].cpu().numpy()
             src = out.src[:kept].cpu().numpy()
-            labels = torch.stack([torch.nn.functional.pad(r["labels"], (0, cap - r["labels"].shape[0])) for r in results]).cpu().numpy()
+            labels = labels_d.cpu().numpy()
             for j in range(kept):
                 k, d = int(src[j]) // cap, int(src[j]) % cap
                 x, y, w, h = xywh[j]

@@ -67,23 +67,38 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~20 us pass. Without
-// the hint the instruction returned after ~300 cycles and the polling loops of 16 single lanes ate 30 % of the SM's
-// issue slots (ncu: 60 M of 197 M executed instructions).
+// try_wait: plain (returns after a short hardware-defined time, the caller polls) or with a suspend-time hint (the
+// thread sleeps in hardware until the phase completes or the hint expires; NANOSLEEP.SYNCS in SASS).
 __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ bool mbar_try_wait_hint(unsigned bar, unsigned parity, unsigned ns) {
     unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity), "r"(ns)
         : "memory");
     return ok != 0;
 }
 // A wait that cannot hang the GPU: a barrier that never completes (a protocol bug) traps after seconds.
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+// sleep_ns > 0: suspend-hint variant.
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity, unsigned sleep_ns = 0) {
     unsigned spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 20)) __trap();
+    if (sleep_ns) {
+        while (!mbar_try_wait_hint(bar, parity, sleep_ns)) {
+            if (++spins > (1u << 22)) __trap();
+        }
+    } else {
+        while (!mbar_try_wait(bar, parity)) {
+            if (++spins > (1u << 24)) __trap();
+        }
     }
 }
 __device__ __forceinline__ void st_shared(unsigned addr, float v) {
@@ -93,8 +108,8 @@ __device__ __forceinline__ void st_shared(unsigned addr, float v) {
 // costs ~32 cycles of the SM's shared-memory atomic path (measured: with every lane of 14 consumer warps polling,
 // the barrier traffic alone bounded the kernel at ~5.7 us per RoI); shared memory has no per-thread caches, so the
 // lanes released by the warp barrier read what the polling lane was allowed to read.
-__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity, int lane) {
-    if (lane == 0) mbar_wait(bar, parity);
+__device__ __forceinline__ void mbar_wait_warp(unsigned bar, unsigned parity, int lane, unsigned sleep_ns = 0) {
+    if (lane == 0) mbar_wait(bar, parity, sleep_ns);
     __syncwarp();
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
@@ -342,7 +357,7 @@ __global__ void __launch_bounds__(256) k_roi_geom(const __grid_constant__ mb_roi
 }
 
 struct TmaSmem {          // carve-up of the dynamic shared memory (offsets in bytes)
-    unsigned ring, ob, geom, rowoff, bars, total;
+    unsigned ring, ob, geom, rowoff, cum, rel, bars, total;
 };
 __host__ __device__ inline TmaSmem tma_smem_layout(unsigned ring_bytes, unsigned ob_bytes) {
     TmaSmem s;
@@ -350,8 +365,10 @@ __host__ __device__ inline TmaSmem tma_smem_layout(unsigned ring_bytes, unsigned
     s.ob = ring_bytes;
     s.geom = s.ob + 2 * ob_bytes;
     s.rowoff = s.geom + kGeomSlots * (unsigned)sizeof(TmaGeom);
-    s.bars = s.rowoff + kRowSlots * 4;
-    s.total = s.bars + (2 * kRowSlots + 2 * kGeomSlots + 4) * 8;
+    s.cum = s.rowoff + kRowSlots * 4;
+    s.rel = s.cum + kRowSlots * 4;
+    s.bars = s.rel + 16 * 4;
+    s.total = s.bars + (kRowSlots + 2 * kGeomSlots + 4) * 8;
     return s;
 }
 
@@ -367,13 +384,14 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
     TmaGeom* geom = reinterpret_cast<TmaGeom*>(smem_raw + L.geom);
     volatile int* rowoff = reinterpret_cast<volatile int*>(smem_raw + L.rowoff);
     const unsigned s_base = smem_u32(smem_raw);
-    const unsigned b_full = s_base + L.bars, b_empty = b_full + kRowSlots * 8, b_gfull = b_empty + kRowSlots * 8;
+    volatile unsigned* cumtab = reinterpret_cast<volatile unsigned*>(smem_raw + L.cum);     // bytes allocated up to and including row seq
+    volatile int* relcnt = reinterpret_cast<volatile int*>(smem_raw + L.rel);              // per consumer warp: rows released so far
+    const unsigned b_full = s_base + L.bars, b_gfull = b_full + kRowSlots * 8;
     const unsigned b_gempty = b_gfull + kGeomSlots * 8, b_ofull = b_gempty + kGeomSlots * 8, b_ofree = b_ofull + 16;
 
     if (tid == 0) {
         for (int i = 0; i < kRowSlots; ++i) {
             mbar_init(b_full + 8 * i, 1);
-            mbar_init(b_empty + 8 * i, kTmaConsumers);
         }
         for (int i = 0; i < kGeomSlots; ++i) {
             mbar_init(b_gfull + 8 * i, 1);
@@ -383,21 +401,23 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
             mbar_init(b_ofull + 8 * i, kTmaConsumers);
             mbar_init(b_ofree + 8 * i, 1);
         }
+        for (int i = 0; i < 16; ++i) relcnt[i] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    const unsigned slp = ((unsigned)dbg >> 8) & 0xffffu;      // probe: suspend-time hint of the waits in ns (0 = poll)
     const int my_rois = blockIdx.x < num_rois ? (num_rois - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp == kTmaConsumers) {
         // =========================== producer: record prefetch + TMA row copies ===========================
         if (lane == 0) {          // a single thread: allocation is sequential, and every mbarrier / bulk-copy op is per thread
-            int next_seq = 0, tail_seq = 0;
-            unsigned head = 0;
+            int next_seq = 0, freed_seq = 0;              // rows issued / rows known to be released by every consumer warp
+            unsigned head = 0, cum_head = 0, cum_freed = 0, spins = 0;   // ring write offset; bytes allocated / reclaimed so far (mod 2^32)
             auto fetch_record = [&](int j) {          // record of this CTA's j-th RoI -> slot j % kGeomSlots
                 if (j >= my_rois) return;
                 const int slot = j % kGeomSlots, use = j / kGeomSlots;
-                if (use >= 1) mbar_wait(b_gempty + 8 * slot, (use - 1) & 1);        // consumers are done with the slot's previous record
+                if (use >= 1) mbar_wait(b_gempty + 8 * slot, (use - 1) & 1, slp);        // consumers are done with the slot's previous record
                 mbar_arrive_expect_tx(b_gfull + 8 * slot, (unsigned)sizeof(TmaGeom));
                 bulk_g2s(s_base + L.geom + slot * (unsigned)sizeof(TmaGeom), recs + (blockIdx.x + (size_t)j * gridDim.x),
                          (unsigned)sizeof(TmaGeom), b_gfull + 8 * slot);
@@ -409,28 +429,30 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
             for (int it = 0; it < my_rois; ++it) {
                 fetch_record(it + kGeomSlots - 2);
                 const int gs = it % kGeomSlots;
-                mbar_wait(b_gfull + 8 * gs, (it / kGeomSlots) & 1);
+                mbar_wait(b_gfull + 8 * gs, (it / kGeomSlots) & 1, slp);
                 const TmaGeom& G = geom[gs];
                 if (G.mode != 1) continue;
                 const int nrows = G.nrows;
                 const unsigned size = G.rowbytes;
                 const char* img = reinterpret_cast<const char*>(G.img);
-                // ---- stream the touched rows into the ring (FIFO byte ring, rows never split) ----
+                // ---- stream the touched rows into the ring (FIFO byte ring, rows never split). This loop is ONE thread:
+                //      it must stay a few dozen instructions per row (a first version with a general allocator and an
+                //      mbarrier wait per row took ~550 cycles per row and bounded the whole kernel). Space accounting is a
+                //      byte-credit counter; consumers publish "rows released" in one word per warp, read only when the
+                //      credits run out. ----
                 for (int rr = 0; rr < nrows; ++rr) {
-                    unsigned off;
-                    for (;;) {
-                        if (tail_seq == next_seq) { head = 0; off = 0; break; }      // nothing live
-                        const unsigned tail_off = (unsigned)rowoff[tail_seq & (kRowSlots - 1)];
-                        if (next_seq - tail_seq < kRowSlots) {
-                            if (head > tail_off) {
-                                if (head + size <= ring_bytes) { off = head; break; }
-                                if (size <= tail_off) { off = 0; break; }
-                            } else if (head + size <= tail_off) { off = head; break; }
-                        }
-                        mbar_wait(b_empty + 8 * (tail_seq & (kRowSlots - 1)), (tail_seq >> 6) & 1);   // oldest row released by all consumers
-                        ++tail_seq;
+                    unsigned off = head, charged = size;
+                    if (off + size > ring_bytes) { charged += ring_bytes - off; off = 0; }     // wrap: the gap is charged to this row
+                    while (cum_head + charged - cum_freed > ring_bytes || next_seq - freed_seq >= kRowSlots) {
+                        int m = relcnt[0];
+#pragma unroll
+                        for (int q = 1; q < kTmaConsumers; ++q) m = min(m, relcnt[q]);
+                        if (m > freed_seq) { freed_seq = m; cum_freed = cumtab[(m - 1) & (kRowSlots - 1)]; }
+                        else if (++spins > (1u << 26)) __trap();
                     }
                     const int slot = next_seq & (kRowSlots - 1);
+                    cum_head += charged;
+                    cumtab[slot] = cum_head;
                     rowoff[slot] = (int)off;
                     if (dbg & 1) mbar_arrive(b_full + 8 * slot);          // probe: no copies
                     else {
@@ -448,7 +470,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
             for (int it = 0; it < my_rois; ++it) {
                 const int b = it & 1;
                 const size_t k = blockIdx.x + (size_t)it * gridDim.x;
-                mbar_wait(b_ofull + 8 * b, (it >> 1) & 1);
+                mbar_wait(b_ofull + 8 * b, (it >> 1) & 1, slp);
                 if (!(dbg & 4)) bulk_s2g(out + k * C * nbins, s_base + L.ob + b * ob_bytes, ob_bytes);   // probe bit 2: no stores
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the buffer may be rewritten
                 mbar_arrive(b_ofree + 8 * b);
@@ -474,10 +496,10 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
         unsigned ocol = 0;
         for (int it = 0; it < my_rois; ++it) {
             const int gs = it % kGeomSlots, b = it & 1, u = it >> 1;
-            mbar_wait_warp(b_gfull + 8 * gs, (it / kGeomSlots) & 1, lane);
+            mbar_wait_warp(b_gfull + 8 * gs, (it / kGeomSlots) & 1, lane, slp);
             const TmaGeom& G = geom[gs];
             const int mode = G.mode, nrows = G.nrows;
-            if (u >= 1) mbar_wait_warp(b_ofree + 8 * b, (u - 1) & 1, lane);
+            if (u >= 1) mbar_wait_warp(b_ofree + 8 * b, (u - 1) & 1, lane, slp);
             const unsigned ob_u32 = s_base + L.ob + b * ob_bytes;
             auto load_x = [&](int pw, int half) {
                 const uint4 xo = G.xoff[pw];
@@ -505,7 +527,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                         if (lane == 0)
                             for (int q = waited; q < need; ++q) {
                                 const int s = seq0 + q;
-                                mbar_wait(b_full + 8 * (s & (kRowSlots - 1)), (s >> 6) & 1);
+                                mbar_wait(b_full + 8 * (s & (kRowSlots - 1)), (s >> 6) & 1, slp);
                             }
                         __syncwarp();
                         waited = need;
@@ -569,9 +591,9 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                         }
                     }
                     if (mode == 1 && released < rel) {
+                        // every lane has consumed its taps (the bin's results were stored above), so the rows can be overwritten
                         __syncwarp();
-                        if (lane == 0)
-                            for (int q = released; q < rel; ++q) mbar_arrive(b_empty + 8 * ((seq0 + q) & (kRowSlots - 1)));
+                        if (lane == 0) relcnt[warp] = seq0 + rel;
                         released = rel;
                     }
                 }

@@ -71,8 +71,9 @@ def _postprocess_detections(self, class_logits: Tensor, box_regression: Tensor, 
                             image_shapes: List[Tuple[int, int]]):
     """RoIHeads.postprocess_detections (tv:models/detection/roi_heads.py:680-737)."""
     cfg = DetConfig.from_model(self, trick_numel=self._miso_b200_rule)
-    if isinstance(proposals, LazyProposals) and not proposals.materialised:
-        # logits / regression rows are strided by the proposal capacity (the pooler ran on the padded layout)
+    if isinstance(proposals, LazyProposals) and class_logits.shape[0] == proposals.padded.shape[0] * proposals.padded.shape[1]:
+        # logits / regression rows are strided by the proposal capacity: the pooler ran on the padded layout (had somebody
+        # iterated the list before pooling, the pooler would have produced the reference's packed rows instead)
         out = detection.postprocess_detections(class_logits, box_regression, proposals.padded, proposals.counts,
                                                image_shapes, cfg, packed=False)
     else:

@@ -60,7 +60,16 @@ def test_patched_model_matches_reference_stage_by_stage(kind):
     patched_pp = model.roi_heads.postprocess_detections
 
     def spy_pp(class_logits, box_regression, proposals, image_shapes):
-        cap["logits"], cap["reg"] = class_logits.detach().cpu(), box_regression.detach().cpu()
+        # the patched forward never waits for the proposal counts: `proposals` is a LazyProposals and the pooler ran on
+        # its padded [N, R, 4] layout, so logits / regression have N*R rows (rows beyond an image's count are ignored)
+        from miso_b200.patch import LazyProposals
+        assert isinstance(proposals, LazyProposals)
+        n_img, cap_r = proposals.padded.shape[:2]
+        assert class_logits.shape[0] == n_img * cap_r
+        cnt = proposals.counts.tolist()
+        live = torch.cat([torch.arange(c) + i * cap_r for i, c in enumerate(cnt)])
+        cap["live_rows"] = live
+        cap["logits"], cap["reg"] = class_logits.detach().cpu()[live], box_regression.detach().cpu()[live]
         cap["proposals"], cap["shapes"] = [p.detach().cpu() for p in proposals], list(image_shapes)
         res = patched_pp(class_logits, box_regression, proposals, image_shapes)
         cap["pp_out"] = [[t.detach().cpu() for t in r] for r in res]
@@ -136,7 +145,11 @@ def test_patched_model_matches_reference_stage_by_stage(kind):
     # RoIAlign: bit-exact against torchvision's CPU pooler on identical inputs
     with torch.inference_mode():
         ref_pool = cpu.roi_heads.box_roi_pool(cap["pool_in"][0], cap["pool_in"][1], cap["pool_in"][2])
-    assert torch.equal(cap["pool_out"], ref_pool)
+    assert cap["pool_out"].shape[0] == len(imgs) * model.rpn.post_nms_top_n()     # padded layout, no RoI tensor was built
+    assert torch.equal(cap["pool_out"][cap["live_rows"]], ref_pool)
+    dead = torch.ones(cap["pool_out"].shape[0], dtype=torch.bool)
+    dead[cap["live_rows"]] = False
+    assert not cap["pool_out"][dead].any()
     # detection post-processing on identical inputs
     with torch.inference_mode():
         rb, rs, rl = cpu.roi_heads.postprocess_detections(cap["logits"], cap["reg"], cap["proposals"], cap["shapes"])
@@ -252,37 +265,68 @@ def test_cli_infer_directory_writes_reference_crops(tmp_path):
 
 
 def test_infer_mosaic_equals_per_tile_composition():
-    """Config 5 driver on a small mosaic (4 overlapping tiles): its result must equal the explicit
-    composition: per-tile detections of the same model -> + tile origin -> score filter -> the
-    oracle's per-class NMS -> the oracle's crops."""
+    """Config 5 driver on a small mosaic (4 overlapping tiles): its result must equal the explicit composition:
+    per-tile detections of the same model -> + tile origin -> score filter -> the oracle's per-class NMS -> miso's
+    rounding + numpy slices of the mosaic (tests/mosaic_ref.py)."""
     from miso_b200 import mosaic
-    from miso_b200.patch import patch_model
+    from miso_b200.patch import forward_uint8, patch_model
+    from tests import mosaic_ref as R
     model = patch_model(make_model("faster").to(DEV))
     g = torch.Generator().manual_seed(5)
     mos = torch.randint(0, 256, (1536, 1536, 3), dtype=torch.uint8, generator=g)
     mos_dev = mos.to(DEV)
     thr = 0.3
-    fb, fs, fl, crops = mosaic.infer_mosaic(model, mos_dev, tile=1024, overlap=128, threshold=thr, batch_size=2)
+    res = mosaic.infer_mosaic(model, mos_dev, (1536, 1536), tile=1024, overlap=128, threshold=thr, batch_size=2)
     grid = mosaic.tile_grid(1536, 1536, 1024, 128)
     assert grid == [(0, 0), (0, 512), (512, 0), (512, 512)]
-    allb, alls, alll = [], [], []
+    dpi = int(model.roi_heads.detections_per_img)
+    block = np.zeros((4 * dpi, 6), np.float32)
+    block[:, 5] = -1
     with torch.inference_mode():
         for i0 in range(0, 4, 2):
             # the same forward infer_mosaic uses (fused uint8 input transform); the float path differs from it by
             # ~1e-6 at the backbone input (torchvision's CUDA interpolate), which a random-init model amplifies
-            from miso_b200.patch import forward_uint8
             tiles = [mos_dev[y:y + 1024, x:x + 1024] for y, x in grid[i0:i0 + 2]]
-            for (y, x), r in zip(grid[i0:i0 + 2], forward_uint8(model, tiles)):
+            for t, ((y, x), r) in enumerate(zip(grid[i0:i0 + 2], forward_uint8(model, tiles))):
                 off = torch.tensor([x, y, x, y], dtype=torch.float32, device=DEV)
-                m = r["scores"] > thr
-                allb.append((r["boxes"] + off)[m]); alls.append(r["scores"][m]); alll.append(r["labels"][m])
-    B, S, L = torch.cat(allb).cpu().numpy(), torch.cat(alls).cpu().numpy(), torch.cat(alll).cpu().numpy()
-    from oracle import detection as D
-    keep = D.batched_nms_vanilla(B, S, L, float(model.roi_heads.nms_thresh))
-    assert np.array_equal(fb.cpu().numpy(), B[keep]) and np.array_equal(fl.cpu().numpy(), L[keep])
+                k = r["boxes"].shape[0]
+                rows = block[(i0 + t) * dpi:(i0 + t) * dpi + k]
+                rows[:, :4] = (r["boxes"] + off).cpu().numpy()
+                rows[:, 4] = r["scores"].cpu().numpy()
+                rows[:, 5] = np.where(r["scores"].cpu().numpy() > np.float32(thr), r["labels"].cpu().numpy().astype(np.float32), -1.0)
+    assert np.array_equal(res["gathered"].cpu().numpy(), block)
+    keep = R.seam_keep_rows(block, float(model.roi_heads.nms_thresh))
     assert len(keep) > 0
-    got = crops.to_host(3)
-    _, _, _, _, _, ref = M.filter_and_crop(mos.numpy(), B[keep], np.ones(len(keep), np.float32), L[keep], 0.5)
-    assert len(got) == len(ref)
-    for (_, _, _, a), r in zip(got, ref):
-        assert np.array_equal(a, r)
+    assert np.array_equal(np.nonzero(res["state"].cpu().numpy() == 1)[0], keep)
+    xywh, ci, ref = R.crops_of_rows(mos.numpy(), block, keep)
+    c = res["crops"]
+    assert c["count"] == len(keep) and np.array_equal(c["src"].cpu().numpy(), keep) and np.array_equal(c["xywh"].cpu().numpy(), xywh)
+    rects, offs, pix = c["rects"].cpu().numpy(), c["offsets"].cpu().numpy(), c["pixels"].cpu().numpy()
+    for j, r in enumerate(ref):
+        assert np.array_equal(pix[offs[j]:offs[j + 1]].reshape(rects[j][3], rects[j][2], 3), r)
+
+
+def test_patched_model_runs_channels_last_and_never_syncs_before_the_results():
+    """patch_model moves backbone + FPN to torch.channels_last, so cuDNN hands the pooler NHWC maps (gathered in place
+    by the TMA-staged RoIAlign kernel: no transpose launch), and the RPN hands over a LazyProposals that nobody
+    materialises during the forward pass."""
+    from miso_b200 import _lib
+    from miso_b200.patch import LazyProposals, patch_model
+    model = patch_model(make_model("faster").to(DEV))
+    seen = {}
+    pool = model.roi_heads.box_roi_pool
+
+    def pre_hook(mod, inp):
+        feats = [v for k, v in inp[0].items() if k in mod.featmap_names]
+        seen["nhwc"] = all((not f.is_contiguous()) and f.is_contiguous(memory_format=torch.channels_last) for f in feats)
+        seen["lazy"] = isinstance(inp[1], LazyProposals) and not inp[1].materialised
+        seen["props"] = inp[1]
+    h = pool.register_forward_pre_hook(pre_hook)
+    n0 = _lib.load().mb_roi_align_tma_launches()
+    with torch.inference_mode():
+        out = model([im.to(DEV) for im in images()])
+    h.remove()
+    assert seen["nhwc"] and seen["lazy"]
+    assert not seen["props"].materialised                      # the whole forward ran without reading the proposal counts
+    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1   # the box pooler took the TMA-staged kernel
+    assert len(out) == 2 and out[0]["boxes"].shape[1] == 4

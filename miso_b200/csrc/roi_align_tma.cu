@@ -159,11 +159,22 @@ __device__ __forceinline__ float2 sample2(float2 w1, float2 w2, float2 w3, float
     }
 }
 
+// the 16 weight products of a bin, w[4 * sample + corner] (each duplicated for the packed arithmetic): computed once
+// per bin and shared by every 128-channel pass over it
+__device__ __forceinline__ void bin_weights(const float2 (&wy)[4], const float2 (&wx)[4], float2 (&W)[16]) {
+#pragma unroll
+    for (int smp = 0; smp < 4; ++smp) {
+        const int iy = smp >> 1, ix = smp & 1;
+        const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
+        W[4 * smp + 0] = mul2_rn(hyv, hxv); W[4 * smp + 1] = mul2_rn(hyv, lxv);
+        W[4 * smp + 2] = mul2_rn(lyv, hxv); W[4 * smp + 3] = mul2_rn(lyv, lxv);
+    }
+}
+
 // All four samples valid: the 16 taps are the product of the bin's distinct rows and columns (patterns of
 // axis_pattern: 0 = both samples in one cell, 1 = they share a pixel, 2 = four pixels); each distinct pixel is loaded once.
 template <bool EXACT, int PY, int PX, typename RowT>
-__device__ __forceinline__ float4 bin_fast(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&wy)[4],
-                                           const float2 (&wx)[4], float2 ones) {
+__device__ __forceinline__ float4 bin_fast(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&W)[16], float2 ones) {
     constexpr int NR = PY == 0 ? 2 : (PY == 1 ? 3 : 4), NC = PX == 0 ? 2 : (PX == 1 ? 3 : 4);
     float4 G[NR][NC];
 #pragma unroll
@@ -176,13 +187,11 @@ __device__ __forceinline__ float4 bin_fast(const RowT (&rb)[4], const unsigned (
         const int iy = smp >> 1, ix = smp & 1;
         const int yl = iy == 0 ? 0 : (PY == 0 ? 0 : (PY == 1 ? 1 : 2)), yh = iy == 0 ? 1 : (PY == 0 ? 1 : (PY == 1 ? 2 : 3));
         const int xl = ix == 0 ? 0 : (PX == 0 ? 0 : (PX == 1 ? 1 : 2)), xh = ix == 0 ? 1 : (PX == 0 ? 1 : (PX == 1 ? 2 : 3));
-        const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
-        const float2 w1 = mul2_rn(hyv, hxv), w2 = mul2_rn(hyv, lxv), w3 = mul2_rn(lyv, hxv), w4 = mul2_rn(lyv, lxv);
         const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
-        lo = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y),
-                            make_float2(v4.x, v4.y), lo, ones);
-        hi = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w),
-                            make_float2(v4.z, v4.w), hi, ones);
+        lo = sample2<EXACT>(W[4 * smp], W[4 * smp + 1], W[4 * smp + 2], W[4 * smp + 3], make_float2(v1.x, v1.y),
+                            make_float2(v2.x, v2.y), make_float2(v3.x, v3.y), make_float2(v4.x, v4.y), lo, ones);
+        hi = sample2<EXACT>(W[4 * smp], W[4 * smp + 1], W[4 * smp + 2], W[4 * smp + 3], make_float2(v1.z, v1.w),
+                            make_float2(v2.z, v2.w), make_float2(v3.z, v3.w), make_float2(v4.z, v4.w), hi, ones);
     }
     const float2 q = make_float2(0.25f, 0.25f);     // acc / 4 samples: exact scaling
     lo = mul2_rn(lo, q);
@@ -198,25 +207,23 @@ __device__ __forceinline__ T slot_sel(const T (&a)[4], int i) {      // a[i] wit
 }
 
 template <bool EXACT, typename RowT>
-__device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&wy)[4],
-                                              const float2 (&wx)[4], int py, int px, int yvalid, int xvalid, float2 ones) {
+__device__ __forceinline__ float4 bin_generic(const RowT (&rb)[4], const unsigned (&co)[4], const float2 (&W)[16], int py, int px,
+                                              int yvalid, int xvalid, float2 ones) {
     float2 lo = make_float2(0.f, 0.f), hi = make_float2(0.f, 0.f);
 #pragma unroll
     for (int smp = 0; smp < 4; ++smp) {
         const int iy = smp >> 1, ix = smp & 1;
         if (!((yvalid >> iy) & 1) || !((xvalid >> ix) & 1)) continue;       // warp-uniform
-        const float2 hyv = wy[2 * iy], lyv = wy[2 * iy + 1], hxv = wx[2 * ix], lxv = wx[2 * ix + 1];
-        const float2 w1 = mul2_rn(hyv, hxv), w2 = mul2_rn(hyv, lxv), w3 = mul2_rn(lyv, hxv), w4 = mul2_rn(lyv, lxv);
         // slots of the second sample follow the axis pattern: (0,1), (1,2) or (2,3)
         const int ys = iy ? py : 0, xs = ix ? px : 0;
         const RowT rlo = slot_sel(rb, ys), rhi = slot_sel(rb, ys + 1);
         const unsigned clo = slot_sel(co, xs), chi = slot_sel(co, xs + 1);
         const float4 v1 = tap_ld(rlo, clo), v2 = tap_ld(rlo, chi);
         const float4 v3 = tap_ld(rhi, clo), v4 = tap_ld(rhi, chi);
-        lo = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.x, v1.y), make_float2(v2.x, v2.y), make_float2(v3.x, v3.y),
-                            make_float2(v4.x, v4.y), lo, ones);
-        hi = sample2<EXACT>(w1, w2, w3, w4, make_float2(v1.z, v1.w), make_float2(v2.z, v2.w), make_float2(v3.z, v3.w),
-                            make_float2(v4.z, v4.w), hi, ones);
+        lo = sample2<EXACT>(W[4 * smp], W[4 * smp + 1], W[4 * smp + 2], W[4 * smp + 3], make_float2(v1.x, v1.y),
+                            make_float2(v2.x, v2.y), make_float2(v3.x, v3.y), make_float2(v4.x, v4.y), lo, ones);
+        hi = sample2<EXACT>(W[4 * smp], W[4 * smp + 1], W[4 * smp + 2], W[4 * smp + 3], make_float2(v1.z, v1.w),
+                            make_float2(v2.z, v2.w), make_float2(v3.z, v3.w), make_float2(v4.z, v4.w), hi, ones);
     }
     const float2 q = make_float2(0.25f, 0.25f);
     lo = mul2_rn(lo, q);
@@ -479,21 +486,20 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
         }
     } else {
         // =========================== consumers ===========================
+        // Task = one bin (ph, pw), ALL channels: the bin's control state (row waits, tap addresses, the 16 weight
+        // products) is set up once and shared by the 128-channel passes (lane = 4 consecutive channels). Bins are dealt
+        // round-robin to the warps and the deal continues across RoIs (49 bins over 14 warps: 4 / 3 per RoI, evened out
+        // by the next RoI); warps only meet at the output hand-over.
         const int halves = (C + 127) >> 7;
-        const int T = PW * halves;                    // tasks per pooled row; task t = (half t / PW, pooled column t % PW)
-        const bool one_task = T <= kTmaConsumers;     // detection box head: 7 columns x 2 halves = one task per warp and pooled row
-        const int first_half = warp / PW, first_pw = warp - first_half * PW;
         const int rot4 = lane >> 3;
         unsigned so4[4];                              // byte offsets of the rotated channel rows in the output buffer
 #pragma unroll
         for (int t = 0; t < 4; ++t) so4[t] = (unsigned)(((rot4 + t) & 3) * nbins) * 4u;
         const unsigned ring_lane = s_base + L.ring + lane * 16;
+        const int dph = kTmaConsumers / PW, dpw = kTmaConsumers - dph * PW;      // one task step in (ph, pw)
+        const unsigned half_out = 128u * (unsigned)nbins * 4u;                    // output bytes per 128-channel pass
         int seq0 = 0;                                 // sequence number of the current RoI's first staged row
-        // per-task state of the pooled column: tap column offsets (+ the channel half), weights, pattern, output column
-        unsigned co[4];
-        float2 wx[4];
-        int px = 0, xv = 0, c0 = 0;
-        unsigned ocol = 0;
+        int next_bin = warp;                          // this warp's first bin in the current RoI
         for (int it = 0; it < my_rois; ++it) {
             const int gs = it % kGeomSlots, b = it & 1, u = it >> 1;
             mbar_wait_warp(b_gfull + 8 * gs, (it / kGeomSlots) & 1, lane, slp);
@@ -501,28 +507,29 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
             const int mode = G.mode, nrows = G.nrows;
             if (u >= 1) mbar_wait_warp(b_ofree + 8 * b, (u - 1) & 1, lane, slp);
             const unsigned ob_u32 = s_base + L.ob + b * ob_bytes;
-            auto load_x = [&](int pw, int half) {
-                const uint4 xo = G.xoff[pw];
-                const float4 xa = G.xwa[pw], xb = G.xwb[pw];
-                const unsigned hoff = (unsigned)half * 512u;
-                co[0] = xo.x + hoff; co[1] = xo.y + hoff; co[2] = xo.z + hoff; co[3] = xo.w + hoff;
-                wx[0] = make_float2(xa.x, xa.y); wx[1] = make_float2(xa.z, xa.w);
-                wx[2] = make_float2(xb.x, xb.y); wx[3] = make_float2(xb.z, xb.w);
-                const int xi = G.xinfo[pw];
-                px = xi & 3; xv = (xi >> 2) & 3;
-                c0 = half * 128 + 4 * lane;
-                ocol = ob_u32 + (unsigned)(c0 * nbins + pw) * 4u;
-            };
             if (mode == 0) {
                 float4* o4 = reinterpret_cast<float4*>(smem_raw + L.ob + b * ob_bytes);
                 for (unsigned i = warp * 32 + lane; i < ob_bytes / 16; i += kTmaConsumers * 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                int waited = 0, released = 0;
+            } else if (!(dbg & 2)) {                                                       // probe bit 1: no arithmetic
+                int waited = 0, published = 0;
                 const char* gimg = reinterpret_cast<const char*>(G.img) + lane * 16;
-                if (one_task && warp < T) load_x(first_pw, first_half);
-                for (int ph = 0; ph < PH; ++ph) {
+                int ph = next_bin / PW, pw = next_bin - ph * PW, cur_pw = -1;
+                unsigned co[4];
+                float2 wx[4];
+                int px = 0, xv = 0;
+                for (int bin = next_bin; bin < nbins; bin += kTmaConsumers) {
+                    if (pw != cur_pw) {
+                        cur_pw = pw;
+                        const uint4 xo = G.xoff[pw];
+                        const float4 xa = G.xwa[pw], xb = G.xwb[pw];
+                        co[0] = xo.x; co[1] = xo.y; co[2] = xo.z; co[3] = xo.w;
+                        wx[0] = make_float2(xa.x, xa.y); wx[1] = make_float2(xa.z, xa.w);
+                        wx[2] = make_float2(xb.x, xb.y); wx[3] = make_float2(xb.z, xb.w);
+                        const int xi = G.xinfo[pw];
+                        px = xi & 3; xv = (xi >> 2) & 3;
+                    }
                     const int yi = G.yinfo[ph];
-                    const int need = (yi >> 8) & 0xff, rel = (yi >> 16) & 0xff;
+                    const int need = (yi >> 8) & 0xff;
                     if (mode == 1 && waited < need) {
                         if (lane == 0)
                             for (int q = waited; q < need; ++q) {
@@ -532,73 +539,80 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                         __syncwarp();
                         waited = need;
                     }
-                    if (!(dbg & 2) && warp < T) {                                            // probe bit 1: no arithmetic
-                        const int4 yx = G.yidx[ph];
-                        const float4 ya = G.ywa[ph], yb = G.ywb[ph];
-                        const float2 wy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y),
-                                              make_float2(yb.z, yb.w)};
-                        const int py = yi & 3, yv = (yi >> 2) & 3;
-                        const unsigned orow = (unsigned)(ph * PW) * 4u;
-                        int pw = first_pw, half = first_half;
-                        if (mode == 1) {
-                            // slots of invalid samples are never read (their ordinals are 0: some staged row's offset)
-                            unsigned rs[4];
-                            rs[0] = ring_lane + (unsigned)rowoff[(seq0 + yx.x) & (kRowSlots - 1)];
-                            rs[1] = ring_lane + (unsigned)rowoff[(seq0 + yx.y) & (kRowSlots - 1)];
-                            rs[2] = ring_lane + (unsigned)rowoff[(seq0 + yx.z) & (kRowSlots - 1)];
-                            rs[3] = ring_lane + (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)];
-                            for (int t = warp; t < T; t += kTmaConsumers) {
-                                if (!one_task) load_x(pw, half);
-                                if (c0 < C) {
-                                    float4 av;
-                                    if (yv == 3 && xv == 3) {
-                                        switch (py * 3 + px) {      // warp-uniform
-                                            case 0: av = bin_fast<EXACT, 0, 0>(rs, co, wy, wx, ones); break;
-                                            case 1: av = bin_fast<EXACT, 0, 1>(rs, co, wy, wx, ones); break;
-                                            case 2: av = bin_fast<EXACT, 0, 2>(rs, co, wy, wx, ones); break;
-                                            case 3: av = bin_fast<EXACT, 1, 0>(rs, co, wy, wx, ones); break;
-                                            case 4: av = bin_fast<EXACT, 1, 1>(rs, co, wy, wx, ones); break;
-                                            case 5: av = bin_fast<EXACT, 1, 2>(rs, co, wy, wx, ones); break;
-                                            case 6: av = bin_fast<EXACT, 2, 0>(rs, co, wy, wx, ones); break;
-                                            case 7: av = bin_fast<EXACT, 2, 1>(rs, co, wy, wx, ones); break;
-                                            default: av = bin_fast<EXACT, 2, 2>(rs, co, wy, wx, ones); break;
-                                        }
-                                    } else {
-                                        av = bin_generic<EXACT>(rs, co, wy, wx, py, px, yv, xv, ones);
+                    const int4 yx = G.yidx[ph];
+                    const float4 ya = G.ywa[ph], yb = G.ywb[ph];
+                    const float2 wy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y),
+                                          make_float2(yb.z, yb.w)};
+                    const int py = yi & 3, yv = (yi >> 2) & 3;
+                    float2 W[16];
+                    bin_weights(wy, wx, W);
+                    const unsigned obin = ob_u32 + (unsigned)(4 * lane * nbins + bin) * 4u;
+                    if (mode == 1) {
+                        // slots of invalid samples are never read (their ordinals are 0: some staged row's offset)
+                        unsigned rs[4];
+                        rs[0] = ring_lane + (unsigned)rowoff[(seq0 + yx.x) & (kRowSlots - 1)];
+                        rs[1] = ring_lane + (unsigned)rowoff[(seq0 + yx.y) & (kRowSlots - 1)];
+                        rs[2] = ring_lane + (unsigned)rowoff[(seq0 + yx.z) & (kRowSlots - 1)];
+                        rs[3] = ring_lane + (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)];
+                        const bool fast = yv == 3 && xv == 3;
+                        const int pat = py * 3 + px;
+                        for (int h = 0; h < halves; ++h) {
+                            if (h * 128 + 4 * lane < C) {
+                                float4 av;
+                                if (fast) {
+                                    switch (pat) {      // warp-uniform
+                                        case 0: av = bin_fast<EXACT, 0, 0>(rs, co, W, ones); break;
+                                        case 1: av = bin_fast<EXACT, 0, 1>(rs, co, W, ones); break;
+                                        case 2: av = bin_fast<EXACT, 0, 2>(rs, co, W, ones); break;
+                                        case 3: av = bin_fast<EXACT, 1, 0>(rs, co, W, ones); break;
+                                        case 4: av = bin_fast<EXACT, 1, 1>(rs, co, W, ones); break;
+                                        case 5: av = bin_fast<EXACT, 1, 2>(rs, co, W, ones); break;
+                                        case 6: av = bin_fast<EXACT, 2, 0>(rs, co, W, ones); break;
+                                        case 7: av = bin_fast<EXACT, 2, 1>(rs, co, W, ones); break;
+                                        default: av = bin_fast<EXACT, 2, 2>(rs, co, W, ones); break;
                                     }
-                                    rotate4(av, rot4);
-                                    const unsigned o = ocol + orow;
-                                    st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
-                                    st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
+                                } else {
+                                    av = bin_generic<EXACT>(rs, co, W, py, px, yv, xv, ones);
                                 }
-                                pw += kTmaConsumers;
-                                while (pw >= PW) { pw -= PW; ++half; }
+                                rotate4(av, rot4);
+                                const unsigned o = obin + (unsigned)h * half_out;
+                                st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
+                                st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
                             }
-                        } else {
-                            const char* rg[4] = {gimg + (unsigned)yx.x, gimg + (unsigned)yx.y, gimg + (unsigned)yx.z, gimg + (unsigned)yx.w};
-                            for (int t = warp; t < T; t += kTmaConsumers) {
-                                if (!one_task) load_x(pw, half);
-                                if (c0 < C) {
-                                    float4 av = bin_generic<EXACT>(rg, co, wy, wx, py, px, yv, xv, ones);
-                                    rotate4(av, rot4);
-                                    const unsigned o = ocol + orow;
-                                    st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
-                                    st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
-                                }
-                                pw += kTmaConsumers;
-                                while (pw >= PW) { pw -= PW; ++half; }
+                            rs[0] += 512u; rs[1] += 512u; rs[2] += 512u; rs[3] += 512u;      // next 128 channels of the same pixels
+                        }
+                    } else {
+                        const char* rg[4] = {gimg + (unsigned)yx.x, gimg + (unsigned)yx.y, gimg + (unsigned)yx.z, gimg + (unsigned)yx.w};
+                        for (int h = 0; h < halves; ++h) {
+                            if (h * 128 + 4 * lane < C) {
+                                float4 av = bin_generic<EXACT>(rg, co, W, py, px, yv, xv, ones);
+                                rotate4(av, rot4);
+                                const unsigned o = obin + (unsigned)h * half_out;
+                                st_shared(o + so4[0], av.x); st_shared(o + so4[1], av.y);
+                                st_shared(o + so4[2], av.z); st_shared(o + so4[3], av.w);
                             }
+                            rg[0] += 512; rg[1] += 512; rg[2] += 512; rg[3] += 512;
                         }
                     }
-                    if (mode == 1 && released < rel) {
-                        // every lane has consumed its taps (the bin's results were stored above), so the rows can be overwritten
-                        __syncwarp();
-                        if (lane == 0) relcnt[warp] = seq0 + rel;
-                        released = rel;
+                    // advance to this warp's next bin; rows that neither it nor any later bin needs can go
+                    ph += dph; pw += dpw;
+                    if (pw >= PW) { pw -= PW; ++ph; }
+                    if (mode == 1) {
+                        const int keep_from = ph >= PH ? nrows : (ph == 0 ? 0 : (G.yinfo[ph - 1] >> 16) & 0xff);
+                        if (keep_from > published) {
+                            __syncwarp();               // every lane has consumed its taps (their results were stored above)
+                            if (lane == 0) relcnt[warp] = seq0 + keep_from;
+                            published = keep_from;
+                        }
                     }
                 }
+            }
+            if (mode == 1) {
+                __syncwarp();
+                if (lane == 0) relcnt[warp] = seq0 + nrows;      // (also for warps that had no bin in this RoI)
                 seq0 += nrows;
             }
+            next_bin = (next_bin >= nbins ? next_bin : next_bin + ((nbins - 1 - next_bin) / kTmaConsumers + 1) * kTmaConsumers) - nbins;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the bulk copy
             __syncwarp();
             if (lane == 0) {

@@ -263,6 +263,28 @@ int mb_seam_select(const float* block, const int32_t* state, int64_t row_lo, int
                    float* boxes_out, float* scores_out, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Training-side siblings (reached from ref:miso/object_detection/engine/engine.py:33
+ * `model(images, targets)`).
+ *  mb_box_iou       torchvision.ops.box_iou (tv:ops/boxes.py:299-330): boxes1 [n1,4], boxes2 [n2,4] -> [n1,n2].
+ *  mb_match_encode  assign_targets_to_anchors / assign_targets_to_proposals fused (tv:models/detection/rpn.py:193-229,
+ *                   roi_heads.py:580-614): Matcher (_utils.py:345-426) on box_iou(gt, anchors) without materialising
+ *                   the [M,N] matrix + BoxCoder.encode_single (_utils.py:85-127) of gt[matches.clamp(min=0)].
+ *                   matches_out [N] int64 (gt index, -1 below low, -2 between), matched_vals_out [N] (nullable),
+ *                   targets_out [N,4] (nullable). num_gt >= 1 (the reference handles empty targets in Python).
+ *  mb_roi_align_backward  torchvision::_roi_align_backward (tv-csrc:ops/cuda/roi_align_kernel.cu): grad [K,C,PH,PW],
+ *                   rois [K,5] -> grad_input [batch,C,H,W] (NCHW, zero-filled by the call, then atomically accumulated).
+ * ------------------------------------------------------------------------------------ */
+int mb_box_iou(const float* boxes1, int64_t n1, const float* boxes2, int64_t n2, float* iou_out, mb_stream_t stream);
+size_t mb_match_encode_workspace_bytes(int64_t num_gt, int64_t num_anchors);
+int mb_match_encode(const float* gt_boxes, int64_t num_gt, const float* anchors, int64_t num_anchors,
+                    float high_threshold, float low_threshold, int32_t allow_low_quality_matches, float wx, float wy,
+                    float ww, float wh, int64_t* matches_out, float* matched_vals_out, float* targets_out,
+                    void* workspace, size_t workspace_bytes, mb_stream_t stream);
+int mb_roi_align_backward(const float* grad, const float* rois, int64_t num_rois, float spatial_scale, int32_t channels,
+                          int32_t height, int32_t width, int32_t pooled_h, int32_t pooled_w, int32_t sampling_ratio,
+                          int32_t aligned, int32_t batch_size, float* grad_input, mb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * paste_masks_in_image (tv:models/detection/roi_heads.py:375-501, called from
  * GeneralizedRCNNTransform.postprocess tv:models/detection/transform.py:269-272).
  * masks [R, 1, M, M] fp32 mask probabilities, boxes [R, 4] fp32 xyxy in image coordinates ->

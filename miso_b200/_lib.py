@@ -107,6 +107,10 @@ SIGNATURES = {
     "mb_seam_nms_workspace_bytes": (_sz, [_i64, _i32, _i64]),
     "mb_seam_nms": (C.c_int, [_p, _i64, _i32, _f64, _i64, _p, _p, _p, _p, _sz, _p]),
     "mb_seam_select": (C.c_int, [_p, _p, _i64, _i64, _p, _p, _p]),
+    "mb_box_iou": (C.c_int, [_p, _i64, _p, _i64, _p, _p]),
+    "mb_match_encode_workspace_bytes": (_sz, [_i64, _i64]),
+    "mb_match_encode": (C.c_int, [_p, _i64, _p, _i64, _f32, _f32, _i32, _f32, _f32, _f32, _f32, _p, _p, _p, _p, _sz, _p]),
+    "mb_roi_align_backward": (C.c_int, [_p, _p, _i64, _f32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p]),
     "mb_paste_masks": (C.c_int, [_p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p]),
     "mb_image_transform": (C.c_int, [C.POINTER(TransformParams), _p, _p]),
 }

@@ -481,3 +481,51 @@ class MultiScaleRoIAlign(torch.nn.Module):
         rois = _f32c(convert_boxes_to_roi_format(boxes))
         return _roi_align_launch(feats, rois, self.scales, self.thresholds, self.output_size, self.sampling_ratio,
                                  False, self.exact, return_levels, force_gather=self.force_gather)
+
+
+# ------------------------------------------------------------------------------------------
+# training-side siblings
+# ------------------------------------------------------------------------------------------
+def box_iou(boxes1: Tensor, boxes2: Tensor) -> Tensor:
+    """torchvision.ops.box_iou (tv:ops/boxes.py:299-330): [N,4] x [M,4] -> [N,M], the reference's operation order."""
+    _require_cuda(boxes1, "boxes1")
+    _require_cuda(boxes2, "boxes2")
+    b1, b2 = _f32c(boxes1), _f32c(boxes2)
+    out = torch.empty((b1.shape[0], b2.shape[0]), dtype=torch.float32, device=b1.device)
+    _lib.check(_lib.load().mb_box_iou(_ptr(b1), b1.shape[0], _ptr(b2), b2.shape[0], _ptr(out), _stream(b1)), "mb_box_iou")
+    return out
+
+
+def match_and_encode(gt_boxes: Tensor, anchors: Tensor, high_threshold: float, low_threshold: float,
+                     allow_low_quality_matches: bool, weights: Sequence[float], return_targets: bool = True):
+    """Matcher(box_iou(gt_boxes, anchors)) + BoxCoder.encode_single(gt_boxes[matches.clamp(min=0)], anchors) in two
+    launches, without the [M, N] IoU matrix (tv:models/detection/_utils.py:345-426, :85-127; call sites
+    rpn.py:193-229, roi_heads.py:580-614). Returns (matches int64 [N], matched_vals [N], targets [N,4] or None)."""
+    _require_cuda(gt_boxes, "gt_boxes")
+    _require_cuda(anchors, "anchors")
+    if gt_boxes.shape[0] == 0:
+        raise ValueError("No ground-truth boxes available for one of the images during training")   # Matcher's own error
+    g, a = _f32c(gt_boxes), _f32c(anchors)
+    n = a.shape[0]
+    lib = _lib.load()
+    matches = torch.empty((n,), dtype=torch.int64, device=a.device)
+    vals = torch.empty((n,), dtype=torch.float32, device=a.device)
+    targets = torch.empty((n, 4), dtype=torch.float32, device=a.device) if return_targets else None
+    ws = _workspace(lib.mb_match_encode_workspace_bytes(g.shape[0], n), a.device)
+    wx, wy, ww, wh = (float(v) for v in weights)
+    _lib.check(lib.mb_match_encode(_ptr(g), g.shape[0], _ptr(a), n, float(high_threshold), float(low_threshold),
+                                   int(bool(allow_low_quality_matches)), wx, wy, ww, wh, _ptr(matches), _ptr(vals), _ptr(targets),
+                                   _ptr(ws), ws.numel(), _stream(a)), "mb_match_encode")
+    return matches, vals, targets
+
+
+def roi_align_backward(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int, pooled_width: int, batch_size: int,
+                       channels: int, height: int, width: int, sampling_ratio: int, aligned: bool) -> Tensor:
+    """torchvision::_roi_align_backward (same argument order as the dispatcher schema): grad [K,C,PH,PW] -> [B,C,H,W]."""
+    _require_cuda(grad, "grad")
+    g, r = _f32c(grad), _f32c(rois)
+    out = torch.empty((batch_size, channels, height, width), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.load().mb_roi_align_backward(_ptr(g), _ptr(r), r.shape[0], float(spatial_scale), int(channels), int(height),
+                                                 int(width), int(pooled_height), int(pooled_width), int(sampling_ratio),
+                                                 int(bool(aligned)), int(batch_size), _ptr(out), _stream(g)), "mb_roi_align_backward")
+    return out.to(grad.dtype)

@@ -194,6 +194,12 @@ def override_torchvision_ops() -> None:
                        sampling_ratio: int, aligned: bool) -> Tensor:
         return ops.roi_align(input, rois, (int(pooled_height), int(pooled_width)), spatial_scale, sampling_ratio, aligned)
 
+    def roi_align_backward_cuda(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_height: int, pooled_width: int,
+                                batch_size: int, channels: int, height: int, width: int, sampling_ratio: int, aligned: bool) -> Tensor:
+        return ops.roi_align_backward(grad, rois, spatial_scale, int(pooled_height), int(pooled_width), int(batch_size),
+                                      int(channels), int(height), int(width), sampling_ratio, aligned)
+
     lib.impl("nms", nms_cuda, "CUDA", allow_override=True)
     lib.impl("roi_align", roi_align_cuda, "CUDA", allow_override=True)
+    lib.impl("_roi_align_backward", roi_align_backward_cuda, "CUDA", allow_override=True)   # training: torchvision's autograd node calls it
     _dispatch_lib = lib

@@ -42,11 +42,12 @@ def match_rate(a, b, la, lb, tol=1e-3):
     return hit / len(a)
 
 
-@pytest.mark.parametrize("kind", ["faster", "mask"])
-def test_patched_model_matches_reference_stage_by_stage(kind):
+# ("faster", 1, (1024, 1024)) is BASELINE config 1 at full size: one 1024^2 image through the patched Faster R-CNN R50-FPN
+@pytest.mark.parametrize("kind,n_img,size", [("faster", 2, (512, 640)), ("mask", 2, (512, 640)), ("faster", 1, (1024, 1024))])
+def test_patched_model_matches_reference_stage_by_stage(kind, n_img, size):
     from miso_b200.patch import patch_model, unpatch_model
     model = make_model(kind).to(DEV)
-    imgs = [im.to(DEV) for im in images()]
+    imgs = [im.to(DEV) for im in images(n_img, size)]
     cap = {}
 
     # capture the stage inputs of the GPU forward

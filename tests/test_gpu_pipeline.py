@@ -14,10 +14,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def build(n=2, original=320, resized=256, channels=16, post=200, dpi=50, seed=0, exact=True):
+def build(n=2, original=320, resized=256, channels=16, post=200, dpi=50, seed=0, exact=True, layout="nchw"):
     from miso_b200 import pipeline, workload
     w = workload.faster_rcnn_batch(num_images=n, original=original, resized=resized, channels=channels,
-                                   post_nms_top_n=post, detections_per_img=dpi, seed=seed, pin=False)
+                                   post_nms_top_n=post, detections_per_img=dpi, seed=seed, pin=False, features_layout=layout)
     hp = pipeline.HotPath(w.shapes, w.rpn, w.det, threshold=w.threshold, crop_capacity_bytes=32 << 20,
                           exact_roi_align=exact, device=DEV)
     dev = workload.to_device(w, DEV)
@@ -38,6 +38,24 @@ def oracle_run(w):
 @pytest.mark.parametrize("seed", [0, 1])
 def test_hot_path_matches_oracle_composition(seed):
     w, hp = build(seed=seed)
+    check_against_oracle(w, hp)
+
+
+@pytest.mark.parametrize("layout", ["channels_last", "nchw"])
+def test_hot_path_full_size_config2_matches_oracle(layout):
+    """BASELINE config 2 at FULL size (batch 4, 1024^2 -> 800^2, 159 882 anchors / image, 1000 proposals, 256
+    channels, 300 detections) against the oracle composition on all four images, stage by stage: proposal counts and
+    boxes, RoIAlign bit-exact (4000 RoIs x 256 x 7 x 7, on the TMA-staged kernel for channels-last maps), detections,
+    crops byte for byte."""
+    from miso_b200 import _lib
+    w, hp = build(n=4, original=1024, resized=800, channels=256, post=1000, dpi=300, seed=0, layout=layout)
+    n0 = _lib.load().mb_roi_align_tma_launches()
+    check_against_oracle(w, hp)
+    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1      # both layouts end up on the TMA-staged kernel
+    assert hp.features_layout == layout
+
+
+def check_against_oracle(w, hp):
     hp.step()
     torch.cuda.synchronize()
     ref, h = oracle_run(w)

@@ -530,6 +530,17 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                     }
                     const int yi = G.yinfo[ph];
                     const int need = (yi >> 8) & 0xff;
+                    if (mode == 1) {
+                        // Rows below the first one this bin (or any later one) needs can go — published BEFORE waiting for this
+                        // bin's rows: a warp that starts at pooled row 1 must not pin row 0 while it waits (the ring may be
+                        // too small to hold both), and the previous bin's taps have all been consumed (results stored).
+                        const int keep_from = ph == 0 ? 0 : (G.yinfo[ph - 1] >> 16) & 0xff;
+                        if (keep_from > published) {
+                            __syncwarp();
+                            if (lane == 0) relcnt[warp] = seq0 + keep_from;
+                            published = keep_from;
+                        }
+                    }
                     if (mode == 1 && waited < need) {
                         if (lane == 0)
                             for (int q = waited; q < need; ++q) {
@@ -594,17 +605,8 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                             rg[0] += 512; rg[1] += 512; rg[2] += 512; rg[3] += 512;
                         }
                     }
-                    // advance to this warp's next bin; rows that neither it nor any later bin needs can go
-                    ph += dph; pw += dpw;
+                    ph += dph; pw += dpw;           // this warp's next bin
                     if (pw >= PW) { pw -= PW; ++ph; }
-                    if (mode == 1) {
-                        const int keep_from = ph >= PH ? nrows : (ph == 0 ? 0 : (G.yinfo[ph - 1] >> 16) & 0xff);
-                        if (keep_from > published) {
-                            __syncwarp();               // every lane has consumed its taps (their results were stored above)
-                            if (lane == 0) relcnt[warp] = seq0 + keep_from;
-                            published = keep_from;
-                        }
-                    }
                 }
             }
             if (mode == 1) {

@@ -292,6 +292,10 @@ int mb_roi_align_backward(const float* grad, const float* rois, int64_t num_rois
  * ------------------------------------------------------------------------------------ */
 int mb_paste_masks(const float* masks, const float* boxes, int64_t num_masks, int32_t mask_side,
                    int32_t padding, int32_t im_h, int32_t im_w, float* out, mb_stream_t stream);
+/* maskrcnn_inference (tv:models/detection/roi_heads.py:56-82): mask_logits [R, C, M, M], labels [R] int64 ->
+ * out [R, 1, M, M] = sigmoid(mask_logits[r, labels[r]]). Labels outside [0, C) are the caller's error. */
+int mb_mask_prob(const float* mask_logits, const int64_t* labels, int64_t num_masks, int32_t num_classes,
+                 int32_t mask_side, float* out, mb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Input transform: ToTensor (ref:miso/object_detection/inference.py:117) +

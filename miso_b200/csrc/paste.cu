@@ -103,7 +103,35 @@ __global__ void __launch_bounds__(kPasteThreads) k_paste_masks(const float* __re
     }
 }
 
+// maskrcnn_inference (tv:models/detection/roi_heads.py:56-82): sigmoid of the channel the predicted label selects,
+// [R, C, M, M] logits + [R] labels -> [R, 1, M, M] probabilities. One launch that reads only the selected channel
+// (the reference runs sigmoid over all C channels, builds an index and gathers).
+__global__ void __launch_bounds__(256) k_mask_prob(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                                  int num_classes, int plane, long long total, float* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / plane;
+        const int p = (int)(i - r * plane);
+        long long c = labels[r];
+        if (c < 0) c += num_classes;                       // python indexing
+        const float x = logits[((size_t)r * num_classes + (size_t)c) * plane + p];
+        out[i] = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+    }
+}
+
 }  // namespace mb
+
+extern "C" int mb_mask_prob(const float* mask_logits, const int64_t* labels, int64_t num_masks, int32_t num_classes,
+                            int32_t mask_side, float* out, mb_stream_t stream) {
+    if (num_masks < 0 || num_classes < 1 || mask_side < 1) return MB_ERR_INVALID_ARG;
+    if (num_masks == 0) return MB_OK;
+    if (!mask_logits || !labels || !out) return MB_ERR_INVALID_ARG;
+    const int plane = mask_side * mask_side;
+    const long long total = num_masks * (long long)plane;
+    const int grid = (int)min((long long)mb::kNumSMs * 8, (total + 255) / 256);
+    mb::k_mask_prob<<<grid, 256, 0, (cudaStream_t)stream>>>(mask_logits, (const long long*)labels, num_classes, plane, total, out);
+    MB_LAUNCH_CHECK();
+    return MB_OK;
+}
 
 extern "C" int mb_paste_masks(const float* masks, const float* boxes, int64_t num_masks, int32_t mask_side, int32_t padding,
                               int32_t im_h, int32_t im_w, float* out, mb_stream_t stream) {

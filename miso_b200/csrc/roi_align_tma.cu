@@ -418,58 +418,78 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
 
     if (warp == kTmaConsumers) {
         // =========================== producer: record prefetch + TMA row copies ===========================
-        if (lane == 0) {          // a single thread: allocation is sequential, and every mbarrier / bulk-copy op is per thread
-            int next_seq = 0, freed_seq = 0;              // rows issued / rows known to be released by every consumer warp
-            unsigned head = 0, cum_head = 0, cum_freed = 0, spins = 0;   // ring write offset; bytes allocated / reclaimed so far (mod 2^32)
-            auto fetch_record = [&](int j) {          // record of this CTA's j-th RoI -> slot j % kGeomSlots
-                if (j >= my_rois) return;
-                const int slot = j % kGeomSlots, use = j / kGeomSlots;
+        // The whole warp works on one RoI: lane j owns footprint row j. Placement in the FIFO byte ring has a closed
+        // form (rows of one RoI have one size and never split: n1 rows fit before the wrap, then laps of nl rows), so the
+        // lanes compute their offsets and "bytes allocated so far" in parallel; a row is issued once the byte credits
+        // cover it. Consumers publish "rows released" in one word per warp; one poll (a load + a 5-step shuffle min)
+        // can release several rows at once. A first version with a sequential allocator and an mbarrier wait per row,
+        // all on one thread, took ~550 cycles per row and bounded the whole kernel.
+        int next_seq = 0;                                  // rows issued so far
+        unsigned head = 0, cum_head = 0;                   // ring write offset; bytes allocated so far (mod 2^32)
+        unsigned spins = 0;
+        auto fetch_record = [&](int j) {          // record of this CTA's j-th RoI -> slot j % kGeomSlots
+            if (j >= my_rois) return;
+            const int slot = j % kGeomSlots, use = j / kGeomSlots;
+            if (lane == 0) {
                 if (use >= 1) mbar_wait(b_gempty + 8 * slot, (use - 1) & 1, slp);        // consumers are done with the slot's previous record
                 mbar_arrive_expect_tx(b_gfull + 8 * slot, (unsigned)sizeof(TmaGeom));
                 bulk_g2s(s_base + L.geom + slot * (unsigned)sizeof(TmaGeom), recs + (blockIdx.x + (size_t)j * gridDim.x),
                          (unsigned)sizeof(TmaGeom), b_gfull + 8 * slot);
-            };
-            // Records are fetched two RoIs ahead into a 4-slot ring: the slot reused at iteration `it` held RoI it-2,
-            // which the consumers finished long ago (the row ring only lets the producer run ~one RoI ahead), so this
-            // wait never stalls the row stream.
-            for (int j = 0; j < kGeomSlots - 2; ++j) fetch_record(j);
-            for (int it = 0; it < my_rois; ++it) {
-                fetch_record(it + kGeomSlots - 2);
-                const int gs = it % kGeomSlots;
-                mbar_wait(b_gfull + 8 * gs, (it / kGeomSlots) & 1, slp);
-                const TmaGeom& G = geom[gs];
-                if (G.mode != 1) continue;
-                const int nrows = G.nrows;
-                const unsigned size = G.rowbytes;
-                const char* img = reinterpret_cast<const char*>(G.img);
-                // ---- stream the touched rows into the ring (FIFO byte ring, rows never split). This loop is ONE thread:
-                //      it must stay a few dozen instructions per row (a first version with a general allocator and an
-                //      mbarrier wait per row took ~550 cycles per row and bounded the whole kernel). Space accounting is a
-                //      byte-credit counter; consumers publish "rows released" in one word per warp, read only when the
-                //      credits run out. ----
-                for (int rr = 0; rr < nrows; ++rr) {
-                    unsigned off = head, charged = size;
-                    if (off + size > ring_bytes) { charged += ring_bytes - off; off = 0; }     // wrap: the gap is charged to this row
-                    while (cum_head + charged - cum_freed > ring_bytes || next_seq - freed_seq >= kRowSlots) {
-                        int m = relcnt[0];
-#pragma unroll
-                        for (int q = 1; q < kTmaConsumers; ++q) m = min(m, relcnt[q]);
-                        if (m > freed_seq) { freed_seq = m; cum_freed = cumtab[(m - 1) & (kRowSlots - 1)]; }
-                        else if (++spins > (1u << 26)) __trap();
-                    }
-                    const int slot = next_seq & (kRowSlots - 1);
-                    cum_head += charged;
-                    cumtab[slot] = cum_head;
-                    rowoff[slot] = (int)off;
-                    if (dbg & 1) mbar_arrive(b_full + 8 * slot);          // probe: no copies
-                    else {
-                        mbar_arrive_expect_tx(b_full + 8 * slot, size);
-                        bulk_g2s(s_base + L.ring + off, img + G.rowsrc[rr], size, b_full + 8 * slot);
-                    }
-                    head = off + size;
-                    ++next_seq;
-                }
             }
+        };
+        // Records are fetched two RoIs ahead into a 4-slot ring: the slot reused at iteration `it` held RoI it-2.
+        for (int j = 0; j < kGeomSlots - 2; ++j) fetch_record(j);
+        for (int it = 0; it < my_rois; ++it) {
+            fetch_record(it + kGeomSlots - 2);
+            const int gs = it % kGeomSlots;
+            mbar_wait_warp(b_gfull + 8 * gs, (it / kGeomSlots) & 1, lane, slp);
+            const TmaGeom& G = geom[gs];
+            if (G.mode != 1) continue;
+            const int nrows = G.nrows;
+            const unsigned size = G.rowbytes;
+            const char* img = reinterpret_cast<const char*>(G.img);
+            const unsigned n1 = (ring_bytes - head) / size;            // rows that still fit before the ring wraps
+            const unsigned nl = ring_bytes / size;                     // rows per lap after that
+            const unsigned gap1 = ring_bytes - head - n1 * size, gapl = ring_bytes - nl * size;
+            unsigned last_off = head, last_cum = cum_head;
+            for (int j0 = 0; j0 < nrows; j0 += 32) {
+                const unsigned j = (unsigned)(j0 + lane);
+                bool pending = (int)j < nrows;
+                unsigned off, cum_end;
+                if (j < n1) { off = head + j * size; cum_end = cum_head + (j + 1) * size; }
+                else {
+                    const unsigned q = j - n1, lap = q / nl, pos = q - lap * nl;
+                    off = pos * size;
+                    cum_end = cum_head + (j + 1) * size + gap1 + lap * gapl;       // the skipped gaps are charged too
+                }
+                const int seq = next_seq + (int)j;
+                const int slot = seq & (kRowSlots - 1);
+                const unsigned src_off = pending ? G.rowsrc[j] : 0u;
+                while (__any_sync(0xffffffffu, pending)) {
+                    int m = lane < kTmaConsumers ? relcnt[lane] : 0x7fffffff;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    const unsigned cum_freed = m > 0 ? cumtab[(m - 1) & (kRowSlots - 1)] : 0u;
+                    const bool ready = pending && (cum_end - cum_freed <= ring_bytes) && (seq - m < kRowSlots);
+                    if (ready) {
+                        cumtab[slot] = cum_end;
+                        rowoff[slot] = (int)off;
+                        if (dbg & 1) mbar_arrive(b_full + 8 * slot);          // probe: no copies
+                        else {
+                            mbar_arrive_expect_tx(b_full + 8 * slot, size);
+                            bulk_g2s(s_base + L.ring + off, img + src_off, size, b_full + 8 * slot);
+                        }
+                        pending = false;
+                    } else if (pending && ++spins > (1u << 26)) __trap();
+                    __syncwarp();
+                }
+                const int last = min(nrows - j0, 32) - 1;               // lane of the last row of this group
+                last_off = __shfl_sync(0xffffffffu, off, last);
+                last_cum = __shfl_sync(0xffffffffu, cum_end, last);
+            }
+            head = last_off + size;
+            cum_head = last_cum;
+            next_seq += nrows;
         }
     } else if (warp == kTmaConsumers + 1) {
         // =========================== store warp: one bulk copy per RoI ===========================

@@ -529,3 +529,19 @@ def roi_align_backward(grad: Tensor, rois: Tensor, spatial_scale: float, pooled_
                                                  int(width), int(pooled_height), int(pooled_width), int(sampling_ratio),
                                                  int(bool(aligned)), int(batch_size), _ptr(out), _stream(g)), "mb_roi_align_backward")
     return out.to(grad.dtype)
+
+
+def maskrcnn_inference(x: Tensor, labels: List[Tensor]) -> List[Tensor]:
+    """tv:models/detection/roi_heads.py:56-82: per image the [R_i, 1, M, M] probabilities of the predicted classes, from
+    the mask head's logits [sum R, C, M, M] — one launch that touches only the selected channels."""
+    _require_cuda(x, "mask logits")
+    torch._assert(x.dim() == 4 and x.shape[2] == x.shape[3], "mask logits should be [R, C, M, M]")
+    per_image = [int(l.shape[0]) for l in labels]
+    lab = torch.cat(list(labels)).to(torch.int64).contiguous()
+    r, c, m = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    torch._assert(lab.shape[0] == r, "one label per mask expected")
+    out = torch.empty((r, 1, m, m), dtype=torch.float32, device=x.device)
+    if r:
+        _lib.check(_lib.load().mb_mask_prob(_ptr(_f32c(x)), _ptr(lab), r, c, m, _ptr(out), _stream(x)), "mb_mask_prob")
+    out = out.to(x.dtype)
+    return list(out.split(per_image, dim=0))

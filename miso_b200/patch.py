@@ -11,6 +11,7 @@ needs autograd, the matcher and the samplers):
     model.roi_heads.box_roi_pool / mask_roi_pool   MultiScaleRoIAlign                -> mb_multiscale_roi_align
     model.roi_heads.postprocess_detections  softmax/decode/clip/filters/NMS/top-k    -> mb_det_postprocess
     model.transform.postprocess             resize_boxes + paste_masks_in_image      -> mb_resize_boxes, mb_paste_masks
+    torchvision...roi_heads.maskrcnn_inference   sigmoid + per-label channel select  -> mb_mask_prob (Mask R-CNN only)
 Hyper-parameters are read from the model instance at call time, never hard-coded.
 """
 from __future__ import annotations
@@ -149,6 +150,19 @@ def patch_model(model, exact_roi_align: bool = True, strategy_rule: str = "cpu",
     if getattr(heads, "mask_roi_pool", None) is not None:
         heads._miso_b200_orig_mask_roi_pool = heads.mask_roi_pool
         heads.mask_roi_pool = ops.MultiScaleRoIAlign.from_torchvision(heads.mask_roi_pool, exact=exact_roi_align)
+    if getattr(heads, "mask_roi_pool", None) is not None:
+        # RoIHeads.forward looks maskrcnn_inference up in its module at call time: route CUDA inputs to the fused kernel
+        import torchvision.models.detection.roi_heads as tv_rh
+        if not hasattr(tv_rh, "_miso_b200_orig_maskrcnn_inference"):
+            tv_rh._miso_b200_orig_maskrcnn_inference = tv_rh.maskrcnn_inference
+
+            def _maskrcnn_inference(x, labels):
+                if x.is_cuda and getattr(tv_rh, "_miso_b200_fused_masks", 0) > 0:
+                    return ops.maskrcnn_inference(x, labels)
+                return tv_rh._miso_b200_orig_maskrcnn_inference(x, labels)
+            tv_rh.maskrcnn_inference = _maskrcnn_inference
+        tv_rh._miso_b200_fused_masks = getattr(tv_rh, "_miso_b200_fused_masks", 0) + 1      # patched models alive
+        model._miso_b200_masks = True
     tr = model.transform
     tr._miso_b200_orig_postprocess = tr.postprocess
     tr.postprocess = types.MethodType(_transform_postprocess, tr)
@@ -167,6 +181,10 @@ def unpatch_model(model):
         h.mask_roi_pool = h._miso_b200_orig_mask_roi_pool
     if hasattr(model.transform, "_miso_b200_orig_postprocess"):
         model.transform.postprocess = model.transform._miso_b200_orig_postprocess
+    if getattr(model, "_miso_b200_masks", False):
+        import torchvision.models.detection.roi_heads as tv_rh
+        tv_rh._miso_b200_fused_masks = max(getattr(tv_rh, "_miso_b200_fused_masks", 1) - 1, 0)
+        model._miso_b200_masks = False
     if getattr(model, "_miso_b200_channels_last", False):
         model.backbone.to(memory_format=torch.contiguous_format)
     model._miso_b200_patched = False

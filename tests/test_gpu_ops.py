@@ -314,3 +314,17 @@ def test_transform_images_gray(ops):
     b, s = ops.transform_images([cu(a) for a in imgs], 128, 200, [0.5], [0.25])
     rb, rs = D.transform_images(imgs, 128, 200, [0.5], [0.25])
     assert s == rs and np.array_equal(b.cpu().numpy(), rb)
+
+
+def test_maskrcnn_inference_selected_channel_sigmoid(ops):
+    """mb_mask_prob against torchvision's maskrcnn_inference (tv:models/detection/roi_heads.py:56-82) on the CPU."""
+    from torchvision.models.detection.roi_heads import maskrcnn_inference as tv_inf
+    tv_inf = getattr(__import__("torchvision.models.detection.roi_heads", fromlist=["x"]), "_miso_b200_orig_maskrcnn_inference", tv_inf)
+    rng = np.random.default_rng(8)
+    x = torch.from_numpy((rng.standard_normal((37, 3, 28, 28)) * 4).astype(np.float32))
+    labels = [torch.from_numpy(rng.integers(1, 3, k)) for k in (20, 0, 17)]
+    ref = tv_inf(x, labels)
+    got = ops.maskrcnn_inference(x.to(DEV), [l.to(DEV) for l in labels])
+    assert [tuple(g.shape) for g in got] == [tuple(r.shape) for r in ref]
+    for g, r in zip(got, ref):
+        assert float((g.cpu() - r).abs().max()) <= 1e-6 if r.numel() else True

@@ -530,7 +530,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
             if (mode == 0) {
                 float4* o4 = reinterpret_cast<float4*>(smem_raw + L.ob + b * ob_bytes);
                 for (unsigned i = warp * 32 + lane; i < ob_bytes / 16; i += kTmaConsumers * 32) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else if (!(dbg & 2)) {                                                       // probe bit 1: no arithmetic
+            } else {
                 int waited = 0, published = 0;
                 const char* gimg = reinterpret_cast<const char*>(G.img) + lane * 16;
                 int ph = next_bin / PW, pw = next_bin - ph * PW, cur_pw = -1;
@@ -587,7 +587,7 @@ k_roi_align_tma(const __grid_constant__ mb_roi_align_params p, const TmaGeom* __
                         rs[3] = ring_lane + (unsigned)rowoff[(seq0 + yx.w) & (kRowSlots - 1)];
                         const bool fast = yv == 3 && xv == 3;
                         const int pat = py * 3 + px;
-                        for (int h = 0; h < halves; ++h) {
+                        for (int h = 0; h < ((dbg & 2) ? 0 : halves); ++h) {      // probe bit 1: no arithmetic
                             if (h * 128 + 4 * lane < C) {
                                 float4 av;
                                 if (fast) {

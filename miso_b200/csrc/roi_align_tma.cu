@@ -357,10 +357,14 @@ __device__ __forceinline__ void build_geom(const mb_roi_align_params& p, const f
 // Pre-pass: the tap tables of every RoI, one warp each, written to the workspace.
 __global__ void __launch_bounds__(256) k_roi_geom(const __grid_constant__ mb_roi_align_params p, const float* __restrict__ rois,
                                                  int num_rois, unsigned row_cap, TmaGeom* __restrict__ recs,
-                                                 int* __restrict__ levels_out) {
+                                                 int* __restrict__ levels_out, int dbg) {
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= num_rois) return;
     build_geom(p, rois, k, row_cap, threadIdx.x & 31, recs[k], levels_out);
+    if (dbg & 16) {                        // probe: RoIs on the direct route produce zeros instead
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0 && recs[k].mode == 2) recs[k].mode = 0;
+    }
 }
 
 struct TmaSmem {          // carve-up of the dynamic shared memory (offsets in bytes)
@@ -704,7 +708,7 @@ int mb_launch_roi_align_tma(const mb_roi_align_params& p, const float* rois, int
                   : cudaFuncSetAttribute(k_roi_align_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_tma_smem));
         attr_set[e] = true;
     }
-    k_roi_geom<<<(unsigned)((num_rois + 7) / 8), 256, 0, stream>>>(p, rois, (int)num_rois, row_cap, recs, levels_out);
+    k_roi_geom<<<(unsigned)((num_rois + 7) / 8), 256, 0, stream>>>(p, rois, (int)num_rois, row_cap, recs, levels_out, dbg);
     MB_LAUNCH_CHECK();
     if (e)
         k_roi_align_tma<true><<<grid, kTmaThreads, L.total, stream>>>(p, recs, (int)num_rois, out, ring, ones, dbg);

@@ -557,7 +557,7 @@ def run_ours(args):
         return med([a_.elapsed_time(b_) for a_, b_ in ev])
 
     other_ms = roi_variant(int(not exact), 0)
-    gather_ms = roi_variant(int(exact), 1)
+    tma_ms = roi_variant(int(exact), 2)
 
     # ---- the same K passes with three batches in flight (the plan's default mode) ----
     ms3, _ = timed(args.steps, False)
@@ -654,7 +654,7 @@ def run_ours(args):
                      "note": "algorithmic bytes are exact per launch (every batch has its own proposals); the event bracket contains both kernels of the call",
                      "limiter": "see DESIGN.md section 7 / profiles/r2_roi_align_tma_ncu_full.txt",
                      "other_mode": {"mode": "fast(fma)" if exact else "exact", "kernel_ms": other_ms, "frac": alg[0][0] / (other_ms * 1e-3) / 1e9 / peak},
-                     "gather_kernel": {"kernel": "k_roi_align_nhwc4d (round 1)", "kernel_ms": gather_ms, "frac": alg[0][0] / (gather_ms * 1e-3) / 1e9 / peak}},
+                     "tma_route": {"kernel": "k_roi_geom+k_roi_align_tma (opt-in, MB_ROI_TMA=1)", "kernel_ms": tma_ms, "frac": alg[0][0] / (tma_ms * 1e-3) / 1e9 / peak}},
         "aggregate": {"bytes_rank0_per_step": rank_bytes, "achieved": rank_bytes / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s",
                       "frac": rank_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                       "frac_pipelined": rank_bytes / (ms3 * 1e-3) / 1e9 / peak,

@@ -630,7 +630,7 @@ constexpr int kChunk4 = 128;   // channels per pass of the 16-byte-gather kernel
 // ------------------------------------------------------------------------------------------
 template <bool EXACT, int PY, int PX>
 __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const uint4 ro4, const uint4 co4,
-                                            const float4* __restrict__ tw) {
+                                            const float4* __restrict__ tw, const float2 ones) {
     constexpr int NR = PY == 0 ? 2 : (PY == 1 ? 3 : 4), NC = PX == 0 ? 2 : (PX == 1 ? 3 : 4);
     const unsigned ro[4] = {ro4.x, ro4.y, ro4.z, ro4.w}, co[4] = {co4.x, co4.y, co4.z, co4.w};
     float4 G[NR][NC];
@@ -651,14 +651,18 @@ __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const u
         const float2 w3 = make_float2(wb.x, wb.y), w4 = make_float2(wb.z, wb.w);
         const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
         if (EXACT) {
-            const float2 p1 = mul2_rn(w1, make_float2(v1.x, v1.y)), p2 = mul2_rn(w2, make_float2(v2.x, v2.y));
-            const float2 p3 = mul2_rn(w3, make_float2(v3.x, v3.y)), p4 = mul2_rn(w4, make_float2(v4.x, v4.y));
-            lo.x = __fadd_rn(lo.x, __fadd_rn(__fadd_rn(__fadd_rn(p1.x, p2.x), p3.x), p4.x));
-            lo.y = __fadd_rn(lo.y, __fadd_rn(__fadd_rn(__fadd_rn(p1.y, p2.y), p3.y), p4.y));
-            const float2 q1 = mul2_rn(w1, make_float2(v1.z, v1.w)), q2 = mul2_rn(w2, make_float2(v2.z, v2.w));
-            const float2 q3 = mul2_rn(w3, make_float2(v3.z, v3.w)), q4 = mul2_rn(w4, make_float2(v4.z, v4.w));
-            hi.x = __fadd_rn(hi.x, __fadd_rn(__fadd_rn(__fadd_rn(q1.x, q2.x), q3.x), q4.x));
-            hi.y = __fadd_rn(hi.y, __fadd_rn(__fadd_rn(__fadd_rn(q1.y, q2.y), q3.y), q4.y));
+            // every product and every sum rounded once, in the reference's order; the sums are packed FFMA2 with an
+            // opaque multiplier 1.0f (fma(p, 1, t) == fl(p + t)), which ptxas cannot contract with the multiplies
+            float2 t = mul2_rn(w1, make_float2(v1.x, v1.y));
+            t = fma2_rn(mul2_rn(w2, make_float2(v2.x, v2.y)), ones, t);
+            t = fma2_rn(mul2_rn(w3, make_float2(v3.x, v3.y)), ones, t);
+            t = fma2_rn(mul2_rn(w4, make_float2(v4.x, v4.y)), ones, t);
+            lo = fma2_rn(t, ones, lo);
+            float2 u = mul2_rn(w1, make_float2(v1.z, v1.w));
+            u = fma2_rn(mul2_rn(w2, make_float2(v2.z, v2.w)), ones, u);
+            u = fma2_rn(mul2_rn(w3, make_float2(v3.z, v3.w)), ones, u);
+            u = fma2_rn(mul2_rn(w4, make_float2(v4.z, v4.w)), ones, u);
+            hi = fma2_rn(u, ones, hi);
         } else {
             lo = __ffma2_rn(w1, make_float2(v1.x, v1.y), __ffma2_rn(w2, make_float2(v2.x, v2.y),
                  __ffma2_rn(w3, make_float2(v3.x, v3.y), __ffma2_rn(w4, make_float2(v4.x, v4.y), lo))));
@@ -671,11 +675,11 @@ __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const u
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
-template <bool EXACT>     // resident CTAs per SM: 3 in exact mode (80 registers, no spills), 4 in FMA mode (64) — measured best
-__global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d(const mb_roi_align_params p,
+template <bool EXACT, int OCC>     // OCC = resident CTAs per SM the register budget is set for
+__global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_roi_align_params p,
                                                                    const float* __restrict__ rois,
                                                                    float* __restrict__ out, int* __restrict__ levels_out,
-                                                                   int rows_per_cta) {
+                                                                   int rows_per_cta, const float2 ones) {
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[32], xtab[32];
     __shared__ uint4 s_ro[16], s_co[16];             // byte offsets of the distinct rows / columns of each bin row / column
@@ -763,15 +767,15 @@ __global__ void __launch_bounds__(kRoiThreads, EXACT ? 3 : 4) k_roi_align_nhwc4d
                 const float4* tw = tab_w + b * 8;
                 float4 av;
                 switch (info >> 16) {      // warp-uniform
-                    case 0: av = bin_dedup<EXACT, 0, 0>(gp, ro4, co4, tw); break;
-                    case 1: av = bin_dedup<EXACT, 0, 1>(gp, ro4, co4, tw); break;
-                    case 2: av = bin_dedup<EXACT, 0, 2>(gp, ro4, co4, tw); break;
-                    case 3: av = bin_dedup<EXACT, 1, 0>(gp, ro4, co4, tw); break;
-                    case 4: av = bin_dedup<EXACT, 1, 1>(gp, ro4, co4, tw); break;
-                    case 5: av = bin_dedup<EXACT, 1, 2>(gp, ro4, co4, tw); break;
-                    case 6: av = bin_dedup<EXACT, 2, 0>(gp, ro4, co4, tw); break;
-                    case 7: av = bin_dedup<EXACT, 2, 1>(gp, ro4, co4, tw); break;
-                    default: av = bin_dedup<EXACT, 2, 2>(gp, ro4, co4, tw); break;
+                    case 0: av = bin_dedup<EXACT, 0, 0>(gp, ro4, co4, tw, ones); break;
+                    case 1: av = bin_dedup<EXACT, 0, 1>(gp, ro4, co4, tw, ones); break;
+                    case 2: av = bin_dedup<EXACT, 0, 2>(gp, ro4, co4, tw, ones); break;
+                    case 3: av = bin_dedup<EXACT, 1, 0>(gp, ro4, co4, tw, ones); break;
+                    case 4: av = bin_dedup<EXACT, 1, 1>(gp, ro4, co4, tw, ones); break;
+                    case 5: av = bin_dedup<EXACT, 1, 2>(gp, ro4, co4, tw, ones); break;
+                    case 6: av = bin_dedup<EXACT, 2, 0>(gp, ro4, co4, tw, ones); break;
+                    case 7: av = bin_dedup<EXACT, 2, 1>(gp, ro4, co4, tw, ones); break;
+                    default: av = bin_dedup<EXACT, 2, 2>(gp, ro4, co4, tw, ones); break;
                 }
                 rotate4(av, rot4);
                 float* o = ob + (4 * lane) * opitch + b;
@@ -925,7 +929,9 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             workspace_bytes -= need;
         }
     }
-    if (p.channels_last && !p.force_gather) {
+    // route: force_gather 0 = library default, 1 = register-gather kernel, 2 = TMA-staged kernel
+    static const bool tma_default = getenv("MB_ROI_TMA") && atoi(getenv("MB_ROI_TMA")) != 0;
+    if (p.channels_last && (p.force_gather == 2 || (p.force_gather == 0 && tma_default))) {
         const int r = mb_launch_roi_align_tma(p, rois, num_rois, out, levels_out, workspace, workspace_bytes, stream);
         if (r == 1) return MB_OK;
         if (r != 0) return r;
@@ -947,13 +953,16 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             const int band = rows * p.pooled_w;
             const int smemd = ((kChunk4 * (band | 1) + 3) & ~3) * (int)sizeof(float) + band * 8 * 16 + band * 4;
             dim3 grid((unsigned)num_rois, (unsigned)ceil_div(p.pooled_h, rows));
-            if (p.exact) {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
-                k_roi_align_nhwc4d<true><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows);
-            } else {
-                MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd));
-                k_roi_align_nhwc4d<false><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows);
-            }
+            const float2 ones = make_float2(1.0f, 1.0f);
+            static const int occ_env = getenv("MB_ROI_OCC") ? atoi(getenv("MB_ROI_OCC")) : 0;      // development switch
+#define MB_NHWC4D(E, O)                                                                                              \
+    do {                                                                                                            \
+        MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd)); \
+        k_roi_align_nhwc4d<E, O><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows, ones);        \
+    } while (0)
+            if (p.exact) { if (occ_env == 3) MB_NHWC4D(true, 3); else MB_NHWC4D(true, 4); }
+            else MB_NHWC4D(false, 4);
+#undef MB_NHWC4D
             MB_LAUNCH_CHECK();
             return MB_OK;
         }

@@ -123,15 +123,6 @@ __device__ __forceinline__ void bulk_s2g(void* dst, unsigned src, unsigned bytes
                  : "memory");
 }
 
-__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;"
-        : "=l"(d)
-        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
-          "l"(reinterpret_cast<unsigned long long&>(c)));
-    return reinterpret_cast<float2&>(d);
-}
-
 // one tap of 4 consecutive channels; RowT = unsigned (shared-memory address) or const char* (global)
 __device__ __forceinline__ float4 tap_ld(unsigned row, unsigned off) {
     float4 v;

@@ -112,4 +112,16 @@ __device__ __forceinline__ int axis_pattern(const Tap& A, const Tap& B, int idx[
 }
 
 
+// Packed fp32x2 fused multiply-add with explicit round-to-nearest (sm_100 FFMA2). fma(p, 1.0f, t) with an OPAQUE 1.0f (a
+// kernel parameter) is an exactly rounded add that ptxas cannot contract with the multiply that produced p.
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+          "l"(reinterpret_cast<unsigned long long&>(c)));
+    return reinterpret_cast<float2&>(d);
+}
+
+
 }  // namespace mb

@@ -49,10 +49,15 @@ def test_hot_path_full_size_config2_matches_oracle(layout):
     crops byte for byte."""
     from miso_b200 import _lib
     w, hp = build(n=4, original=1024, resized=800, channels=256, post=1000, dpi=300, seed=0, layout=layout)
-    n0 = _lib.load().mb_roi_align_tma_launches()
     check_against_oracle(w, hp)
-    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1      # both layouts end up on the TMA-staged kernel
     assert hp.features_layout == layout
+    hp.roi_params.force_gather = 2                                # the TMA-staged route on the same proposals: identical features
+    want = hp.box_features.clone()
+    n0 = _lib.load().mb_roi_align_tma_launches()
+    hp.box_features.zero_()
+    hp.roi_align()
+    torch.cuda.synchronize()
+    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1 and torch.equal(hp.box_features, want)
 
 
 def check_against_oracle(w, hp):

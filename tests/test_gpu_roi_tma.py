@@ -58,9 +58,9 @@ def test_tma_equals_gather_and_oracle_single_level(ops, channels):
     lib = ops._lib.load()
     for exact in (True, False):
         n0 = lib.mb_roi_align_tma_launches()
-        a = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact)
+        a = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather="tma")
         assert lib.mb_roi_align_tma_launches() == n0 + 1          # the TMA-staged kernel produced `a`
-        b = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather=True)
+        b = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather="gather")
         assert lib.mb_roi_align_tma_launches() == n0 + 1          # ... and the gather kernel `b`
         if exact:
             assert torch.equal(a, b)
@@ -68,8 +68,9 @@ def test_tma_equals_gather_and_oracle_single_level(ops, channels):
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(np.abs(x).max()))
     pick = np.sort(rng.choice(rois.shape[0], 96, replace=False))
     ref = native.roi_align(x, rois[pick], 0.25, 7, 7, 2, False)
-    got = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False)[torch.from_numpy(pick).to(DEV)].cpu().numpy()
-    assert np.array_equal(got, ref)
+    for route in ("tma", "gather"):
+        got = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, force_gather=route)[torch.from_numpy(pick).to(DEV)].cpu().numpy()
+        assert np.array_equal(got, ref), route
 
 
 def test_tma_multiscale_many_rois_per_cta(ops):
@@ -82,15 +83,15 @@ def test_tma_multiscale_many_rois_per_cta(ops):
     boxes = [cases.stress_rois(rng, 2000, hw, side=(8.0, 700.0)) for _ in range(n)]
     x = {str(i): cu(f).contiguous(memory_format=torch.channels_last) for i, f in enumerate(feats)}
     tb = [cu(b) for b in boxes]
-    a, la = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2)(x, tb, [hw] * n, return_levels=True)
-    b, lb = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, force_gather=True)(x, tb, [hw] * n, return_levels=True)
+    a, la = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, force_gather="tma")(x, tb, [hw] * n, return_levels=True)
+    b, lb = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, force_gather="gather")(x, tb, [hw] * n, return_levels=True)
     assert torch.equal(la, lb) and set(la.cpu().tolist()) == {0, 1, 2, 3}
     assert torch.equal(a, b)
     pick = np.sort(rng.choice(4000, 80, replace=False))
     sub = [boxes[i][pick[pick // 2000 == i] % 2000] for i in range(n)]
     ref = D.multiscale_roi_align(feats, sub, [hw] * n, 7, 2)
     assert np.array_equal(a[torch.from_numpy(pick).to(DEV)].cpu().numpy(), ref)
-    fast = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, exact=False)(x, tb, [hw] * n)
+    fast = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, exact=False, force_gather="tma")(x, tb, [hw] * n)
     assert torch.allclose(fast, a, rtol=1e-5, atol=5e-5)
 
 
@@ -103,7 +104,7 @@ def test_tma_skips_invalid_samples_like_the_reference(ops):
     x[0, 5, 0, 1] = np.nan
     rois = np.array([[0, 100, 100, 260, 260], [0, -60, 20, 30, 90], [0, 20, -60, 90, 30], [0, 120, 120, 150, 150]], F)
     xc = cu(x).contiguous(memory_format=torch.channels_last)
-    got = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False).cpu().numpy()
+    got = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, force_gather="tma").cpu().numpy()
     ref = native.roi_align(x, rois, 0.25, 7, 7, 2, False)
     assert np.array_equal(got, ref, equal_nan=True)
     assert np.isfinite(got[0]).all() and np.isfinite(got[3]).all()
@@ -123,7 +124,7 @@ def test_tma_per_image_layout_with_dead_rows(ops):
     tf = [cu(f).contiguous(memory_format=torch.channels_last) for f in feats]
     tb, tc = cu(boxes), cu(counts)
     outs = []
-    for force in (0, 1):
+    for force in (2, 1):
         p = RoiAlignParams()
         p.num_levels, p.num_images, p.channels, p.pooled_h, p.pooled_w = 4, n, c, 7, 7
         p.sampling_ratio, p.aligned, p.exact, p.channels_last, p.force_gather = 2, 0, 1, 1, force

@@ -177,6 +177,9 @@ def test_patched_model_matches_reference_stage_by_stage(kind, n_img, size):
         a = model(imgs)
         unpatch_model(model)
         assert model.roi_heads.postprocess_detections == orig_pp
+        # keep the backbone in the memory format the patched run used: cuDNN's NHWC and NCHW convolutions round
+        # differently, and a random-init detector amplifies that into different boxes — not what this compares
+        model.backbone.to(memory_format=torch.channels_last)
         b = model(imgs)
     for x, y in zip(a, b):
         r = match_rate(x["boxes"].cpu().numpy(), y["boxes"].cpu().numpy(), x["labels"].cpu().numpy(), y["labels"].cpu().numpy())

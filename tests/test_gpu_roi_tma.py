@@ -61,14 +61,16 @@ def test_tma_equals_gather_and_oracle_single_level(ops, channels):
         a = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather="tma")
         assert lib.mb_roi_align_tma_launches() == n0 + 1          # the TMA-staged kernel produced `a`
         b = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather="gather")
-        assert lib.mb_roi_align_tma_launches() == n0 + 1          # ... and the gather kernel `b`
+        c = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, exact=exact, force_gather="perbin")
+        assert lib.mb_roi_align_tma_launches() == n0 + 1          # ... and the gather kernels `b`, `c`
+        assert torch.equal(b, c) if exact else torch.allclose(b, c, rtol=1e-5, atol=1e-5 * float(np.abs(x).max()))
         if exact:
             assert torch.equal(a, b)
         else:
             assert torch.allclose(a, b, rtol=1e-5, atol=1e-5 * float(np.abs(x).max()))
     pick = np.sort(rng.choice(rois.shape[0], 96, replace=False))
     ref = native.roi_align(x, rois[pick], 0.25, 7, 7, 2, False)
-    for route in ("tma", "gather"):
+    for route in ("tma", "gather", "perbin"):
         got = ops.roi_align(xc, cu(rois), 7, 0.25, 2, False, force_gather=route)[torch.from_numpy(pick).to(DEV)].cpu().numpy()
         assert np.array_equal(got, ref), route
 

@@ -99,9 +99,9 @@ typedef struct {
      * torch.channels_last cuDNN backbone produces). The kernel then gathers 128-byte channel
      * vectors straight from global memory / L1 and needs no shared-memory staging. */
     int32_t channels_last;
-    /* route for channels-last maps: 0 = library default (the column-sweep register-gather kernel k_roi_align_sweep; the
-     * TMA-staged kernel if the environment variable MB_ROI_TMA=1), 1 = column-sweep kernel, 2 = TMA-staged kernel
-     * (k_roi_geom + k_roi_align_tma), 3 = per-bin register-gather kernel (k_roi_align_nhwc4d). Identical results. */
+    /* route for channels-last maps: 0 = library default (the register-gather kernel k_roi_align_nhwc4d; the TMA-staged
+     * kernel if the environment variable MB_ROI_TMA=1), 1 = register-gather kernel, 2 = TMA-staged kernel
+     * (k_roi_geom + k_roi_align_tma). Identical results. */
     int32_t force_gather;
 } mb_roi_align_params;
 /* Workspace: holds the per-RoI tap-table records of the TMA-staged kernel (channels-last maps, sampling_ratio 2,

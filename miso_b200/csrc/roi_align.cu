@@ -675,6 +675,31 @@ __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const u
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// one bin, samples outside the map skipped like the reference does (no zero-weight multiply: an Inf / NaN feature
+// elsewhere cannot leak in); plain per-sample loads, the reference's operation order in exact mode
+template <bool EXACT>
+__device__ __forceinline__ float4 bin_skip_invalid(const char* __restrict__ gp, const Tap* __restrict__ ytab, const Tap* __restrict__ xtab,
+                                                   int ph, int pw, unsigned rowb, unsigned colb) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < 2; ++iy) {
+        const Tap Y = ytab[2 * ph + iy];
+        if (!Y.valid) continue;
+        for (int ix = 0; ix < 2; ++ix) {
+            const Tap X = xtab[2 * pw + ix];
+            if (!X.valid) continue;
+            const float4 v1 = __ldg(reinterpret_cast<const float4*>(gp + (Y.lo * rowb + X.lo * colb)));
+            const float4 v2 = __ldg(reinterpret_cast<const float4*>(gp + (Y.lo * rowb + X.hi * colb)));
+            const float4 v3 = __ldg(reinterpret_cast<const float4*>(gp + (Y.hi * rowb + X.lo * colb)));
+            const float4 v4 = __ldg(reinterpret_cast<const float4*>(gp + (Y.hi * rowb + X.hi * colb)));
+            acc.x = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.x, v2.x, v3.x, v4.x, acc.x);
+            acc.y = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.y, v2.y, v3.y, v4.y, acc.y);
+            acc.z = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.z, v2.z, v3.z, v4.z, acc.z);
+            acc.w = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.w, v2.w, v3.w, v4.w, acc.w);
+        }
+    }
+    return make_float4(__fmul_rn(acc.x, 0.25f), __fmul_rn(acc.y, 0.25f), __fmul_rn(acc.z, 0.25f), __fmul_rn(acc.w, 0.25f));
+}
+
 template <bool EXACT, int OCC>     // OCC = resident CTAs per SM the register budget is set for
 __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_roi_align_params p,
                                                                    const float* __restrict__ rois,
@@ -738,7 +763,8 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
     __syncthreads();
     for (int b = tid; b < nbins; b += kRoiThreads) {
         const int ph = ph0 + b / PW, pw = b % PW;
-        s_bin[b] = ph | (pw << 8) | ((s_py[ph] * 3 + s_px[pw]) << 16);
+        const bool all_in = ytab[2 * ph].valid && ytab[2 * ph + 1].valid && xtab[2 * pw].valid && xtab[2 * pw + 1].valid;
+        s_bin[b] = ph | (pw << 8) | ((all_in ? s_py[ph] * 3 + s_px[pw] : 9) << 16);     // 9: a sample outside the map -> skipped, not weighted by 0
     }
     __syncthreads();
     const char* img = reinterpret_cast<const char*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C * 4;
@@ -775,7 +801,9 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
                     case 5: av = bin_dedup<EXACT, 1, 2>(gp, ro4, co4, tw, ones); break;
                     case 6: av = bin_dedup<EXACT, 2, 0>(gp, ro4, co4, tw, ones); break;
                     case 7: av = bin_dedup<EXACT, 2, 1>(gp, ro4, co4, tw, ones); break;
-                    default: av = bin_dedup<EXACT, 2, 2>(gp, ro4, co4, tw, ones); break;
+                    case 8: av = bin_dedup<EXACT, 2, 2>(gp, ro4, co4, tw, ones); break;
+                    default: av = bin_skip_invalid<EXACT>(gp, ytab, xtab, info & 0xff, (info >> 8) & 0xff,
+                                                         (unsigned)g.W * (unsigned)C * 4u, (unsigned)C * 4u); break;
                 }
                 rotate4(av, rot4);
                 float* o = ob + (4 * lane) * opitch + b;
@@ -795,255 +823,6 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
         }
         __syncthreads();
         for (int ch = warp; ch < nch; ch += kRoiWarps)
-            for (int b = lane; b < nbins; b += 32) dst[ch * nbins_all + b] = ob[ch * opitch + b];
-        __syncthreads();   // ob is reused by the next chunk
-    }
-    if (bulk && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem must outlive the copies
-}
-
-// ------------------------------------------------------------------------------------------
-// Column sweep (channels-last, sampling_ratio 2, every sample inside the map — the detection path after
-// clip_boxes_to_image). Task = (pooled row, 128 channels), one warp: the warp walks the DISTINCT pixel columns of the
-// RoI's footprint left to right and keeps a window of three columns (x the pooled row's 2..4 distinct pixel rows) in
-// registers — slot j, j+1 in use, j+2 in flight — so every pixel of the pooled row's footprint is loaded ONCE per
-// pass instead of once per bin that taps it (13 x 3 loads instead of 7 x 9 for a typical box-head RoI), which is
-// what the L2->SM fabric, the bound of the per-bin kernel, is charged for. A sample is evaluated when both its
-// columns are present; the two x-samples of a bin may arrive in different steps, so the (iy = 0, 1) partial sums of
-// the first x-sample are held until the second arrives and the four sample sums are then added in the reference's
-// order (iy outer, ix inner) — bit-exact in exact mode (packed FMUL2 / FFMA2 with the opaque 1.0f), FMAs otherwise.
-// RoIs with any sample outside the map take the per-bin kernel (which skips them sample by sample).
-// ------------------------------------------------------------------------------------------
-constexpr int kSweepThreads = 224;      // 7 warps: one per pooled row of a 7-row band (box head 7x7, mask head 2 x 7 rows)
-
-struct SweepSample {      // one x-sample: column slot of its left pixel, duplicated weights for the packed arithmetic
-    int a;
-    float hx, lx;
-    int pad;
-};
-
-template <bool EXACT, int PY>
-__device__ __forceinline__ void sweep_row(const char* __restrict__ gp, const uint4 ro4, const float4 ywt,
-                                          const unsigned* __restrict__ cols, int ncols, const SweepSample* __restrict__ samp,
-                                          int nx, float* __restrict__ orow, const int (&so4)[4], int rot4, const float2 ones) {
-    constexpr int NR = PY == 0 ? 2 : (PY == 1 ? 3 : 4);
-    // row slots of the two y-samples: A uses (0, 1); B uses (0, 1), (1, 2) or (2, 3)
-    constexpr int bl = PY == 0 ? 0 : (PY == 1 ? 1 : 2), bh = bl + 1;
-    const unsigned ro[4] = {ro4.x, ro4.y, ro4.z, ro4.w};
-    const float2 hy0 = make_float2(ywt.x, ywt.x), ly0 = make_float2(ywt.y, ywt.y);
-    const float2 hy1 = make_float2(ywt.z, ywt.z), ly1 = make_float2(ywt.w, ywt.w);
-    float4 W0[NR], W1[NR], W2[NR];
-    auto load_col = [&](float4 (&dst)[NR], int j) {
-        const unsigned c = cols[j];
-#pragma unroll
-        for (int r_ = 0; r_ < NR; ++r_) dst[r_] = __ldg(reinterpret_cast<const float4*>(gp + (ro[r_] + c)));
-    };
-    float2 h0l = make_float2(0.f, 0.f), h0h = h0l, h1l = h0l, h1h = h0l;      // held sums of the bin's first x-sample (iy 0 / 1, channels lo / hi)
-    int s = 0;
-    // one y-sample of one x-sample for two channels: ((w1*v1 + w2*v2) + w3*v3) + w4*v4
-    auto tsum = [&](float2 w1, float2 w2, float2 w3, float2 w4, float2 v1, float2 v2, float2 v3, float2 v4) {
-        if (EXACT) {
-            float2 t = mul2_rn(w1, v1);
-            t = fma2_rn(mul2_rn(w2, v2), ones, t);
-            t = fma2_rn(mul2_rn(w3, v3), ones, t);
-            return fma2_rn(mul2_rn(w4, v4), ones, t);
-        } else {
-            return fma2_rn(w1, v1, fma2_rn(w2, v2, fma2_rn(w3, v3, mul2_rn(w4, v4))));
-        }
-    };
-    auto step = [&](const float4 (&L)[NR], const float4 (&R)[NR], int j) {
-        while (s < nx && samp[s].a == j) {                 // warp-uniform
-            const SweepSample q = samp[s];
-            const float2 hx = make_float2(q.hx, q.hx), lx = make_float2(q.lx, q.lx);
-            const float2 a1 = mul2_rn(hy0, hx), a2 = mul2_rn(hy0, lx), a3 = mul2_rn(ly0, hx), a4 = mul2_rn(ly0, lx);
-            const float2 b1 = mul2_rn(hy1, hx), b2 = mul2_rn(hy1, lx), b3 = mul2_rn(ly1, hx), b4 = mul2_rn(ly1, lx);
-            const float2 t0l = tsum(a1, a2, a3, a4, make_float2(L[0].x, L[0].y), make_float2(R[0].x, R[0].y),
-                                    make_float2(L[1].x, L[1].y), make_float2(R[1].x, R[1].y));
-            const float2 t0h = tsum(a1, a2, a3, a4, make_float2(L[0].z, L[0].w), make_float2(R[0].z, R[0].w),
-                                    make_float2(L[1].z, L[1].w), make_float2(R[1].z, R[1].w));
-            const float2 t1l = tsum(b1, b2, b3, b4, make_float2(L[bl].x, L[bl].y), make_float2(R[bl].x, R[bl].y),
-                                    make_float2(L[bh].x, L[bh].y), make_float2(R[bh].x, R[bh].y));
-            const float2 t1h = tsum(b1, b2, b3, b4, make_float2(L[bl].z, L[bl].w), make_float2(R[bl].z, R[bl].w),
-                                    make_float2(L[bh].z, L[bh].w), make_float2(R[bh].z, R[bh].w));
-            if ((s & 1) == 0) {
-                h0l = t0l; h0h = t0h; h1l = t1l; h1h = t1h;
-            } else {
-                // acc = 0 + s(0,0) + s(0,1) + s(1,0) + s(1,1), one rounding per addition, then / 4
-                const float2 z = make_float2(0.f, 0.f), qv = make_float2(0.25f, 0.25f);
-                float2 lo, hi;
-                if (EXACT) {
-                    lo = fma2_rn(h0l, ones, z); lo = fma2_rn(t0l, ones, lo); lo = fma2_rn(h1l, ones, lo); lo = fma2_rn(t1l, ones, lo);
-                    hi = fma2_rn(h0h, ones, z); hi = fma2_rn(t0h, ones, hi); hi = fma2_rn(h1h, ones, hi); hi = fma2_rn(t1h, ones, hi);
-                } else {
-                    lo = make_float2((h0l.x + t0l.x) + (h1l.x + t1l.x), (h0l.y + t0l.y) + (h1l.y + t1l.y));
-                    hi = make_float2((h0h.x + t0h.x) + (h1h.x + t1h.x), (h0h.y + t0h.y) + (h1h.y + t1h.y));
-                }
-                lo = mul2_rn(lo, qv); hi = mul2_rn(hi, qv);
-                float4 av = make_float4(lo.x, lo.y, hi.x, hi.y);
-                rotate4(av, rot4);
-                float* o = orow + (s >> 1);
-                o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
-            }
-            ++s;
-        }
-    };
-    load_col(W0, 0);
-    load_col(W1, 1);
-    for (int j = 0; j + 1 < ncols; j += 3) {               // static register roles: the window rotates every three columns
-        if (j + 2 < ncols) load_col(W2, j + 2);
-        step(W0, W1, j);
-        if (j + 2 < ncols) {
-            if (j + 3 < ncols) load_col(W0, j + 3);
-            step(W1, W2, j + 1);
-            if (j + 3 < ncols) {
-                if (j + 4 < ncols) load_col(W1, j + 4);
-                step(W2, W0, j + 2);
-            }
-        }
-    }
-}
-
-// one bin, samples outside the map skipped like the reference does (no zero-weight multiply: an Inf / NaN feature
-// elsewhere cannot leak in); plain per-sample loads, the reference's operation order in exact mode
-template <bool EXACT>
-__device__ __forceinline__ float4 bin_skip_invalid(const char* __restrict__ gp, const Tap* __restrict__ ytab, const Tap* __restrict__ xtab,
-                                                   int ph, int pw, unsigned rowb, unsigned colb) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < 2; ++iy) {
-        const Tap Y = ytab[2 * ph + iy];
-        if (!Y.valid) continue;
-        for (int ix = 0; ix < 2; ++ix) {
-            const Tap X = xtab[2 * pw + ix];
-            if (!X.valid) continue;
-            const float4 v1 = __ldg(reinterpret_cast<const float4*>(gp + (Y.lo * rowb + X.lo * colb)));
-            const float4 v2 = __ldg(reinterpret_cast<const float4*>(gp + (Y.lo * rowb + X.hi * colb)));
-            const float4 v3 = __ldg(reinterpret_cast<const float4*>(gp + (Y.hi * rowb + X.lo * colb)));
-            const float4 v4 = __ldg(reinterpret_cast<const float4*>(gp + (Y.hi * rowb + X.hi * colb)));
-            acc.x = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.x, v2.x, v3.x, v4.x, acc.x);
-            acc.y = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.y, v2.y, v3.y, v4.y, acc.y);
-            acc.z = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.z, v2.z, v3.z, v4.z, acc.z);
-            acc.w = bilinear4<EXACT>(Y.h, Y.l, X.h, X.l, v1.w, v2.w, v3.w, v4.w, acc.w);
-        }
-    }
-    return make_float4(__fmul_rn(acc.x, 0.25f), __fmul_rn(acc.y, 0.25f), __fmul_rn(acc.z, 0.25f), __fmul_rn(acc.w, 0.25f));
-}
-
-template <bool EXACT, int OCC>
-__global__ void __launch_bounds__(kSweepThreads, OCC) k_roi_align_sweep(const mb_roi_align_params p, const float* __restrict__ rois,
-                                                                   float* __restrict__ out, int* __restrict__ levels_out,
-                                                                   int rows_per_cta, const float2 ones) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ Tap ytab[32], xtab[32];
-    __shared__ uint4 s_ro[16];
-    __shared__ float4 s_yw[16];
-    __shared__ int s_py[16];
-    __shared__ unsigned s_cols[64];
-    __shared__ __align__(16) SweepSample s_samp[32];
-    __shared__ int s_ncols, s_ok;
-    const int k = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int PH = p.pooled_h, PW = p.pooled_w, nbins_all = PH * PW;
-    const int ph0 = blockIdx.y * rows_per_cta;
-    const int rows = min(rows_per_cta, PH - ph0);
-    const int b0 = ph0 * PW, nbins = rows * PW;
-    const int opitch = (rows_per_cta * PW) | 1;
-    float* ob = smem;                                                  // [128][opitch]
-    float r[5];
-    load_roi(rois, k, p, r);
-    RoiGeom g;
-    roi_geometry(r, p, g);
-    if (levels_out != nullptr && tid == 0 && blockIdx.y == 0) levels_out[k] = g.level;
-    const int ny = PH * 2, nx = PW * 2;
-    if (tid < ny) ytab[tid] = make_tap(g.start_h, g.bin_h, tid >> 1, tid & 1, 2, g.H);
-    if (tid >= 64 && tid < 64 + nx) xtab[tid - 64] = make_tap(g.start_w, g.bin_w, (tid - 64) >> 1, (tid - 64) & 1, 2, g.W);
-    __syncthreads();
-    const int C = p.channels;
-    float* dst_roi = out + (size_t)k * C * nbins_all;
-    if (g.batch < 0 || g.batch >= p.num_images) {
-        if (blockIdx.y == 0) {
-            for (long long i = tid; i < (long long)C * nbins_all; i += blockDim.x) dst_roi[i] = 0.0f;
-        }
-        return;
-    }
-    if (tid == 0) {
-        // distinct pixel columns of the footprint, left to right; a sample clamped to the last column gets a second
-        // entry for the same pixel, so that "right column = slot + 1" holds for every sample
-        bool ok = true;
-        for (int i = 0; i < ny; ++i) ok = ok && ytab[i].valid;
-        for (int i = 0; i < nx; ++i) ok = ok && xtab[i].valid;
-        int n = 0, last = -1;
-        for (int i = 0; i < nx && ok; ++i) {
-            const Tap X = xtab[i];
-            int a;
-            if (n == 0 || X.lo > last) { s_cols[n] = (unsigned)X.lo * (unsigned)C * 4u; a = n++; last = X.lo; }
-            else a = n - 1 - (last - X.lo);                              // X.lo == last or last - 1
-            ok = ok && a >= 0 && (last - X.lo) <= 1;
-            if (a == n - 1) { s_cols[n++] = (unsigned)X.hi * (unsigned)C * 4u; last = X.hi; }
-            s_samp[i].a = a; s_samp[i].hx = X.h; s_samp[i].lx = X.l; s_samp[i].pad = 0;
-            ok = ok && n <= 62;
-        }
-        s_ncols = n;
-        s_ok = ok ? 1 : 0;
-    }
-    if (tid >= 32 && tid < 32 + PH) {
-        const int t = tid - 32;
-        int idx[4];
-        s_py[t] = axis_pattern(ytab[2 * t], ytab[2 * t + 1], idx);
-        const unsigned rb = (unsigned)g.W * (unsigned)C * 4u;
-        s_ro[t] = make_uint4(idx[0] * rb, idx[1] * rb, idx[2] * rb, idx[3] * rb);
-        s_yw[t] = make_float4(ytab[2 * t].h, ytab[2 * t].l, ytab[2 * t + 1].h, ytab[2 * t + 1].l);
-    }
-    __syncthreads();
-    const bool sweep = s_ok != 0;        // false: some sample lies outside the map -> per-bin evaluation that skips it
-    const int ncols = s_ncols;
-    const char* img = reinterpret_cast<const char*>(p.features[g.level]) + (size_t)g.batch * g.H * g.W * C * 4;
-    const int rot4 = lane >> 3;
-    int so4[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) so4[t] = ((rot4 + t) & 3) * opitch;
-    const int nchunks = (C + kChunk4 - 1) / kChunk4;
-    const bool bulk = gridDim.y == 1 && opitch == nbins && ((reinterpret_cast<uintptr_t>(dst_roi) & 15) == 0) &&
-                      ((kChunk4 * nbins) & 3) == 0;
-    for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int c0 = chunk * kChunk4;
-        const int nch = min(kChunk4, C - c0);
-        if (bulk && chunk > 0) {            // the previous chunk's copy must have finished reading the buffer
-            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            __syncthreads();
-        }
-        if (4 * lane < nch) {
-            const char* gp = img + (size_t)(c0 + 4 * lane) * 4;
-            if (!sweep) {
-                const unsigned rowb = (unsigned)g.W * (unsigned)C * 4u, colb = (unsigned)C * 4u;
-                for (int b = warp; b < nbins; b += nwarps) {
-                    float4 av = bin_skip_invalid<EXACT>(gp, ytab, xtab, ph0 + b / PW, b % PW, rowb, colb);
-                    rotate4(av, rot4);
-                    float* o = ob + (4 * lane) * opitch + b;
-                    o[so4[0]] = av.x; o[so4[1]] = av.y; o[so4[2]] = av.z; o[so4[3]] = av.w;
-                }
-            }
-            for (int pr = warp; sweep && pr < rows; pr += nwarps) {
-                const int ph = ph0 + pr;
-                float* orow = ob + (4 * lane) * opitch + pr * PW;
-                switch (s_py[ph]) {      // warp-uniform
-                    case 0: sweep_row<EXACT, 0>(gp, s_ro[ph], s_yw[ph], s_cols, ncols, s_samp, nx, orow, so4, rot4, ones); break;
-                    case 1: sweep_row<EXACT, 1>(gp, s_ro[ph], s_yw[ph], s_cols, ncols, s_samp, nx, orow, so4, rot4, ones); break;
-                    default: sweep_row<EXACT, 2>(gp, s_ro[ph], s_yw[ph], s_cols, ncols, s_samp, nx, orow, so4, rot4, ones); break;
-                }
-            }
-        }
-        float* dst = dst_roi + (size_t)c0 * nbins_all + b0;
-        const int total = nch * nbins;
-        if (bulk && (total & 3) == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the async proxy
-            __syncthreads();
-            if (tid == 0) {
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
-                             :: "l"(dst), "r"(smem_u32(ob)), "r"(total * 4) : "memory");
-            }
-            continue;
-        }
-        __syncthreads();
-        for (int ch = warp; ch < nch; ch += nwarps)
             for (int b = lane; b < nbins; b += 32) dst[ch * nbins_all + b] = ob[ch * opitch + b];
         __syncthreads();   // ob is reused by the next chunk
     }
@@ -1204,22 +983,6 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             dim3 grid((unsigned)num_rois, (unsigned)ceil_div(p.pooled_h, rows));
             const float2 ones = make_float2(1.0f, 1.0f);
             static const int occ_env = getenv("MB_ROI_OCC") ? atoi(getenv("MB_ROI_OCC")) : 0;      // development switch
-            static const bool per_bin = getenv("MB_ROI_PERBIN") && atoi(getenv("MB_ROI_PERBIN")) != 0;
-            if (!per_bin && p.force_gather != 3 && rows * 32 <= kSweepThreads) {
-                // column-sweep kernel: one warp per pooled row of the band
-                const int warps = rows < kRoiWarps ? rows : kRoiWarps;
-                const int smems = ((kChunk4 * (band | 1) + 3) & ~3) * (int)sizeof(float);
-#define MB_SWEEP(E, O)                                                                                              \
-    do {                                                                                                            \
-        MB_CUDA(cudaFuncSetAttribute(k_roi_align_sweep<E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smems));  \
-        k_roi_align_sweep<E, O><<<grid, warps * 32, smems, stream>>>(p, rois, out, levels_out, rows, ones);          \
-    } while (0)
-                if (p.exact) { if (occ_env == 2) MB_SWEEP(true, 2); else MB_SWEEP(true, 3); }
-                else { if (occ_env == 2) MB_SWEEP(false, 2); else MB_SWEEP(false, 3); }
-#undef MB_SWEEP
-                MB_LAUNCH_CHECK();
-                return MB_OK;
-            }
 #define MB_NHWC4D(E, O)                                                                                              \
     do {                                                                                                            \
         MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd)); \

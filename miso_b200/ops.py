@@ -366,7 +366,7 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
                 all(f.dtype == torch.float32 and not f.is_contiguous() and
                     f.is_contiguous(memory_format=torch.channels_last) for f in features))
         p.channels_last = int(nhwc)
-        p.force_gather = {False: 0, True: 1, 0: 0, 1: 1, 2: 2, 3: 3, 'auto': 0, 'gather': 1, 'tma': 2, 'perbin': 3}[force_gather]
+        p.force_gather = {False: 0, True: 1, 0: 0, 1: 1, 2: 2, 'auto': 0, 'gather': 1, 'tma': 2}[force_gather]
         if per_image:
             p.boxes_per_image, p.box_counts = per_image, box_counts.data_ptr()
         for i, f in enumerate(features):
@@ -389,8 +389,8 @@ def _roi_align_launch(features: Sequence[Tensor], rois: Tensor, scales: Sequence
 def roi_align(input: Tensor, boxes: Union[Tensor, Sequence[Tensor]], output_size, spatial_scale: float = 1.0,
               sampling_ratio: int = -1, aligned: bool = False, exact: bool = True, force_gather: bool = False) -> Tensor:
     """RoIAlign forward; `exact=True` reproduces the CPU kernel's fp32 operation order bit for bit.
-    `force_gather`: route for channels-last maps — "auto"/False (library default = "gather"), "gather"/True (column-sweep
-    register-gather kernel), "perbin" (per-bin register-gather kernel), "tma" (TMA-staged kernel); identical results."""
+    `force_gather`: route for channels-last maps — "auto"/False (library default = "gather"), "gather"/True (register-gather
+    kernel), "tma" (TMA-staged kernel); identical results."""
     _require_cuda(input, "input")
     check_roi_boxes_shape(boxes)
     rois = boxes if isinstance(boxes, Tensor) else convert_boxes_to_roi_format(boxes)

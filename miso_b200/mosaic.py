@@ -294,9 +294,34 @@ class MosaicPlan:
     def _c(s) -> C.c_void_p:
         return C.c_void_p(s.cuda_stream)
 
-    def run(self, batches, serial: bool = False) -> None:
-        """Enqueue one whole mosaic pass of this rank (no host sync). Results: self.seam.state, self.crops.*"""
-        self.run_tiles(batches, serial=serial)
+    def capture_tiles(self, batches, serial: bool = False) -> None:
+        """Record run_tiles(batches) as a CUDA graph: the ~17 launches per batch of a rank's whole tile phase then cost
+        one host call (`run(graph=True)`). The graph refers to the batches' tensors: keep them alive and in place."""
+        cur = torch.cuda.current_stream(self.dev)
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            self.run_tiles(batches, serial=serial)               # warm-up outside the capture (function attributes, lazy init)
+            side.synchronize()
+            for n in self.used:
+                self.used[n] = [False] * len(self.used[n])       # no waits on events recorded outside the capture
+            with torch.cuda.graph(graph, stream=side):
+                self.run_tiles(batches, serial=serial)
+        cur.wait_stream(side)
+        for n in self.used:
+            self.used[n] = [False] * len(self.used[n])           # (their events were last recorded inside the capture)
+        self._graph, self._graph_keep = graph, batches
+
+    def run(self, batches=None, serial: bool = False, graph: bool = False) -> None:
+        """Enqueue one whole mosaic pass of this rank (no host sync). Results: self.seam.state, self.crops.*
+        graph=True replays the tile phase recorded by capture_tiles()."""
+        if graph:
+            if getattr(self, "_graph", None) is None:
+                raise MisoB200Error("MosaicPlan.run(graph=True): call capture_tiles() first")
+            self._graph.replay()
+        else:
+            self.run_tiles(batches, serial=serial)
         if self.world > 1:
             exchange(self.block, self.world, self.group, out=self.gathered)
         self.run_tail()

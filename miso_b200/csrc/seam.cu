@@ -100,11 +100,15 @@ struct SeamCand {
     int row;
 };
 
+constexpr int kSeamNbCap = 96;          // neighbour tiles listed per round of the pairs kernel
+constexpr int kSeamRegEdges = 4;        // suppressors a thread keeps in registers during the first pass
+
 __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ block, int rows, int rpt, int tiles,
                                                     float thr_up, SeamWs w, int edge_cap) {
     extern __shared__ __align__(16) unsigned char seam_smem[];
     SeamCand* cand = reinterpret_cast<SeamCand*>(seam_smem);
-    __shared__ int s_n, s_base;
+    __shared__ int s_n, s_base, s_nnb, s_more;
+    __shared__ int s_nb[kSeamNbCap];
     __shared__ int s_wcnt[32];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
     if (w.tile_live[t] == 0) {
@@ -128,12 +132,14 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
         mlabel = (int)c.y;
         mine = c.y >= 0.0f;
     }
-
+    // Pass 0 finds every suppressor once, keeps the first kSeamRegEdges of a row in registers and counts them; the
+    // tile then reserves one contiguous edge segment. Pass 1 runs only if some row had more (rare) and writes the rest.
     int my_count = 0, my_off = 0;
+    int reg_e[kSeamRegEdges];
+#pragma unroll
+    for (int e = 0; e < kSeamRegEdges; ++e) reg_e[e] = -1;
     for (int pass = 0; pass < 2; ++pass) {
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        int written = 0;
+        int seen = 0;
         auto process = [&]() {
             const int n = s_n;
             if (mine) {
@@ -141,27 +147,34 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
                     const SeamCand c = cand[i];
                     if (c.label != mlabel) continue;
                     if (!(c.key < mkey || (c.key == mkey && c.row < my_row))) continue;      // c must precede me
+                    // disjoint boxes have IoU 0 (or NaN for two zero-area boxes): never > thr >= 0; skip the division
+                    if (c.box.z < mb_.x || mb_.z < c.box.x || c.box.w < mb_.y || mb_.w < c.box.y) continue;
                     if (!iou_suppresses(c.box, c.area, mb_, marea, thr_up)) continue;
-                    if (pass == 0) ++my_count;
-                    else {
-                        const int slot = my_off + written;
-                        if (slot < edge_cap) w.edges[slot] = make_int2(c.row, my_row);
-                        ++written;
+                    if (pass == 0) {
+#pragma unroll
+                        for (int e = 0; e < kSeamRegEdges; ++e)
+                            if (my_count == e) reg_e[e] = c.row;
+                        ++my_count;
+                    } else {
+                        // the neighbour list's order may differ between the passes, so a row that overflowed its
+                        // registers rewrites its whole segment
+                        const int slot = my_off + seen;
+                        if (my_count > kSeamRegEdges && slot < edge_cap) w.edges[slot] = make_int2(c.row, my_row);
+                        ++seen;
                     }
                 }
             }
         };
-        for (int u = 0; u < tiles; ++u) {
-            if (w.tile_live[u] == 0) continue;
-            if (!boxes_touch(bb, w.tile_bbox[u])) continue;
+        // stage the live rows of tile uu that touch my tile's box, flushing the chunk through process() when full
+        auto stage_tile = [&](int uu) {
             for (int r0 = 0; r0 < rpt; r0 += blockDim.x) {
-                if (s_n + (int)blockDim.x > kSeamChunk) {       // uniform: s_n is read after a barrier
+                if (s_n + (int)blockDim.x > kSeamChunk) {
                     process();
                     __syncthreads();
                     if (tid == 0) s_n = 0;
                     __syncthreads();
                 }
-                const int r = r0 + tid, row = u * rpt + r;
+                const int r = r0 + tid, row = uu * rpt + r;
                 bool ok = r < rpt && row < rows;
                 SeamCand c;
                 if (ok) {
@@ -174,22 +187,44 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
                     c.label = (int)s.y;
                     c.row = row;
                 }
-                // stable block-wide compaction into cand[s_n ...]
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
                 if (lane == 0) s_wcnt[wid] = __popc(m);
                 __syncthreads();
-                int base = s_n;
-                for (int q = 0; q < wid; ++q) base += s_wcnt[q];
+                int base = s_n, tot = 0;
+                for (int q = 0; q < nw; ++q) {
+                    base += q < wid ? s_wcnt[q] : 0;
+                    tot += s_wcnt[q];
+                }
                 if (ok) cand[base + __popc(m & ((1u << lane) - 1u))] = c;
                 __syncthreads();
-                if (tid == 0) {
-                    int tot = 0;
-                    for (int q = 0; q < nw; ++q) tot += s_wcnt[q];
-                    s_n += tot;
-                }
+                if (tid == 0) s_n += tot;
                 __syncthreads();
             }
+        };
+        if (tid == 0) s_n = 0;
+        for (int u0 = 0; u0 < tiles; u0 += blockDim.x) {
+            // neighbour tiles among u0 .. u0 + blockDim.x - 1: every thread tests one tile, the hits go to a short list
+            // (in any order: the edges are a set)
+            __syncthreads();
+            if (tid == 0) s_nnb = 0;
+            __syncthreads();
+            const int u = u0 + tid;
+            if (u < tiles && w.tile_live[u] != 0 && boxes_touch(bb, w.tile_bbox[u])) {
+                const int slot = atomicAdd(&s_nnb, 1);
+                if (slot < kSeamNbCap) s_nb[slot] = u;
+            }
+            __syncthreads();
+            const int nnb = s_nnb;
+            if (nnb <= kSeamNbCap) {
+                for (int k = 0; k < nnb; ++k) stage_tile(s_nb[k]);
+            } else {
+                // more neighbours than the list holds (boxes far larger than a tile): walk the range in order
+                const int u1 = min(u0 + (int)blockDim.x, tiles);
+                for (int uu = u0; uu < u1; ++uu)
+                    if (w.tile_live[uu] != 0 && boxes_touch(bb, w.tile_bbox[uu])) stage_tile(uu);
+            }
         }
+        __syncthreads();
         process();
         __syncthreads();
         if (pass == 0) {
@@ -201,6 +236,7 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
                 if (lane >= o) x += y;
             }
             if (lane == 31) s_wcnt[wid] = x;
+            if (tid == 0) s_more = 0;
             __syncthreads();
             int pre = 0, tot = 0;
             for (int q = 0; q < nw; ++q) { pre += (q < wid) ? s_wcnt[q] : 0; tot += s_wcnt[q]; }
@@ -210,9 +246,13 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
                 w.seg_count[t] = tot;
                 if (s_base + tot > edge_cap) w.counters[1] = 1;
             }
+            if (my_count > kSeamRegEdges) s_more = 1;
             __syncthreads();
             my_off = s_base + pre + x - my_count;
-            if (tot == 0) return;
+#pragma unroll
+            for (int e = 0; e < kSeamRegEdges; ++e)
+                if (e < my_count && my_off + e < edge_cap) w.edges[my_off + e] = make_int2(reg_e[e], my_row);
+            if (tot == 0 || !s_more) return;
         }
     }
 }

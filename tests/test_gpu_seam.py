@@ -126,3 +126,19 @@ def test_sparse_seam_reports_edge_overflow_and_rejects_negative_threshold(mosaic
     assert n == 1 and edges == 4096 * 4095 // 2
     with pytest.raises(MisoB200Error):
         mosaic.SparseSeamNms(4096, 256, DEV).launch(g, -0.1)
+
+
+def test_sparse_seam_more_neighbour_tiles_than_the_list_holds(mosaic):
+    """300 groups of 16 rows whose bounding boxes all touch: the per-tile neighbour list (96 entries) overflows and
+    the pairs kernel walks the tiles in order instead; rows with more than four suppressors take the second pass."""
+    rng = np.random.default_rng(41)
+    n = 16 * 300 + 5
+    c = rng.uniform(0, 700, (n, 2)); s = np.exp(rng.uniform(np.log(30), np.log(260), (n, 2)))
+    block = np.zeros((n, 6), F)
+    block[:, :4] = np.concatenate([c - s / 2, c + s / 2], 1)
+    block[:, 4] = rng.uniform(0, 1, n)
+    block[:, 5] = rng.integers(0, 2, n)
+    block[rng.choice(n, 200, replace=False), 5] = -1
+    keep, edges = run_sparse(mosaic, block, 16, 0.3, edges_per_row=64)
+    assert np.array_equal(keep, R.seam_keep_rows(block, 0.3))
+    assert edges > 4 * n

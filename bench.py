@@ -335,6 +335,8 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_affinity = (mosaic.bind_host_near_gpu(dev) if world > 1 and not os.environ.get("MB_BENCH_NO_BIND")
+                     else {"bound": False, "why": "single process" if world == 1 else "MB_BENCH_NO_BIND"})
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -629,7 +631,7 @@ def run_ours(args):
         hb = torch.tensor([float(runner.h2d_bytes), float(runner.d2h_bytes)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(hb, op=dist.ReduceOp.SUM)
-        e2e = {"value": float(td[0]) / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": int(hb[1]),
+        e2e = {"value": float(td[0]) / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": int(hb[0]), "d2h_bytes_per_step": int(hb[1]), "host_affinity": host_affinity,
                "ms_per_step": 1e3 * float(te[0]), "steps": e2e_steps,
                "h2d_gbs_per_gpu": float(hb[0]) / world / float(te[0]) / 1e9,
                "api": "miso_b200.mosaic.HostMosaicRunner (pinned host in/out; copy-in stream | 3 compute streams | copy-out stream)",

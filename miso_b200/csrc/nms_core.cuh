@@ -279,7 +279,7 @@ __device__ __forceinline__ float4 offset_box(float4 b, float o) {
 // added on load (tv:ops/boxes.py:101); 0 for segments that run the per-group strategy.
 static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
                                                  float thr_up, unsigned long long* __restrict__ mask,
-                                                 const float* __restrict__ seg_offset) {
+                                                 const float* __restrict__ seg_offset, int full) {
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     __shared__ int sh_g, sh_r, sh_c;
@@ -317,10 +317,10 @@ static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restric
         // two threads per row: thread (row, half) tests columns 32*half .. 32*half+31 and writes its own
         // 32-bit half of the mask word (little-endian halves of the 64-bit word)
         const int row = r * 64 + (tid & 63), half = tid >> 6;
+        unsigned int word = 0;
         if (row < n) {
             const float4 a = offset_box(sbox[st + row], off);
             const float area_a = box_area_rn(a);
-            unsigned int word = 0;
             // Diagonal tiles carry the full symmetric word (bits j < row too): the sweep resolves a
             // 64-box block in parallel from "who suppresses me" = word & lower bits.
             const int skip = (r == c) ? (tid & 63) : -1;
@@ -341,6 +341,20 @@ static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restric
                     if (j != skip && iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1u << (j - j0);
             }
             reinterpret_cast<unsigned int*>(mask)[2 * (s.mask_off[g] + (long long)row * T + c) + half] = word;
+        }
+        if (full && r != c) {
+            // the fixed-point sweep reads "who suppresses me" for whole rows: IoU is symmetric, so the tile's transpose
+            // fills word r of rows 64c .. 64c+63. This warp holds rows 32*(warp&1).. of columns 32*half..: one ballot
+            // per column gives that column's 32 row bits; lane j keeps column j's and writes its 32-bit half.
+            const int lane = tid & 31, sub = (tid >> 5) & 1;
+            unsigned int tw = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const unsigned int b = __ballot_sync(0xffffffffu, (word >> j) & 1u);
+                if (lane == j) tw = b;
+            }
+            const int trow = c * 64 + 32 * half + lane;
+            if (trow < n) reinterpret_cast<unsigned int*>(mask)[2 * (s.mask_off[g] + (long long)trow * T + r) + sub] = tw;
         }
         __syncthreads();
     }
@@ -623,6 +637,88 @@ static __global__ void __launch_bounds__(kSweepThreads) k_nms_sweep_wide(SegArra
     if (tid == 0) s.seg_kept[g] = kept;
 }
 
+// ------------------------------------------------------------------------------------
+// sweep for segments of up to 1024 boxes (T <= 16 words), the RPN (image x level) and detection (image x class)
+// case: greedy NMS is the unique fixed point of "kept iff every earlier overlapping box is removed; removed iff one of
+// them is kept" (the lowest undecided box is always decidable), so instead of resolving 64 boxes at a time in order,
+// every box of the segment iterates on it at once: thread t keeps its suppressor words (row t of the full mask, bits
+// below t) in registers, the kept / removed sets live in shared memory as one 32-bit half-word per warp, and a round
+// costs one barrier. Rounds = longest suppression chain of the segment (a handful for detector output; the worst case,
+// a chain through all n boxes, takes n rounds and is still exact). Needs k_nms_mask(full = 1).
+// ------------------------------------------------------------------------------------
+constexpr int kFixThreads = 1024;
+constexpr int kFixWords = kFixThreads / 64;
+
+static __global__ void __launch_bounds__(kFixThreads) k_nms_fixpoint(SegArrays s, const unsigned long long* __restrict__ mask,
+                                                                     unsigned long long* __restrict__ keepbits, int max_keep) {
+    __shared__ __align__(8) unsigned int C32[2 * kFixWords], R32[2 * kFixWords];
+    const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n = s.seg_count[g];
+    const int T = s.seg_words[g];
+    if (n == 0 || s.totals[2] != 0) { if (t == 0) s.seg_kept[g] = 0; return; }
+    const unsigned long long* m = mask + s.mask_off[g] + (long long)t * T;
+    unsigned long long* kb = keepbits + s.keep_off[g];
+    const int nw = min((warp >> 1) + 1, T);                 // words holding boxes before this warp's (warp-uniform)
+    unsigned long long S[kFixWords];
+#pragma unroll
+    for (int w = 0; w < kFixWords; ++w) S[w] = (w < nw && t < n) ? m[w] : 0ull;
+#pragma unroll
+    for (int w = 0; w < kFixWords; ++w)
+        if (w == (t >> 6)) S[w] &= (1ull << (t & 63)) - 1ull;
+    bool decided = t >= n;
+    {
+        const unsigned int inv = __ballot_sync(0xffffffffu, decided);
+        if (lane == 0) { C32[warp] = 0u; R32[warp] = inv; }
+    }
+    __syncthreads();
+    const unsigned long long* Cw = reinterpret_cast<const unsigned long long*>(C32);
+    const unsigned long long* Rw = reinterpret_cast<const unsigned long long*>(R32);
+    while (true) {
+        bool k = false, r = false;
+        if (!decided) {
+            bool hit = false, open = false;
+#pragma unroll
+            for (int w = 0; w < kFixWords; ++w) {
+                if (w < nw) {
+                    const unsigned long long c = Cw[w], rr = Rw[w];
+                    hit |= (S[w] & c) != 0ull;
+                    open |= (S[w] & ~rr) != 0ull;
+                }
+            }
+            r = hit;
+            k = !hit && !open;
+        }
+        const unsigned int bk = __ballot_sync(0xffffffffu, k), br = __ballot_sync(0xffffffffu, r);
+        if (lane == 0 && (bk | br)) { C32[warp] |= bk; R32[warp] |= br; }     // a warp owns its half-word: no atomics
+        decided = decided || k || r;
+        // (a warp that runs ahead may publish round i+1 facts while another still reads round i: the sets only grow
+        // by true facts, so any interleaving converges to the same fixed point)
+        if (!__syncthreads_or(!decided)) break;
+    }
+    if (t == 0) {
+        int kept = 0;
+        for (int b = 0; b < T; ++b) {
+            unsigned long long keepw = Cw[b];
+            if (max_keep > 0) {
+                if (kept >= max_keep) keepw = 0ull;
+                else if (kept + __popcll(keepw) > max_keep) {
+                    int extra = kept + __popcll(keepw) - max_keep;     // trim to exactly max_keep kept boxes
+                    while (extra-- > 0) keepw &= ~(1ull << (63 - __clzll(keepw)));
+                }
+            }
+            kb[b] = keepw;
+            kept += __popcll(keepw);
+        }
+        s.seg_kept[g] = kept;
+    }
+}
+
+// MB_NMS_SWEEP=blocks keeps the 64-box block sweeps for every segment size (development A/B switch)
+inline bool sweep_in_order() {
+    static const bool v = [] { const char* e = getenv("MB_NMS_SWEEP"); return e != nullptr && e[0] == 'b'; }();
+    return v;
+}
+
 inline int sweep_smem_bytes(int max_words) { return max_words * (int)sizeof(unsigned long long); }
 
 // Host helper: launch meta + mask + sweep on prepared sorted boxes.
@@ -630,8 +726,14 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
                                  unsigned long long* mask, unsigned long long* keepbits, int max_keep,
                                  cudaStream_t stream, const float* seg_offset = nullptr) {
     const float thr_up = strict_gt_threshold(iou_threshold);
-    k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset);
+    const bool fix = max_seg_elems <= kFixThreads && !sweep_in_order();
+    k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset, fix ? 1 : 0);
     MB_LAUNCH_CHECK();
+    if (fix) {
+        k_nms_fixpoint<<<G, kFixThreads, 0, stream>>>(s, mask, keepbits, max_keep);
+        MB_LAUNCH_CHECK();
+        return MB_OK;
+    }
     // (the cp.async ring kernel below measured 8-12 % slower than this one at <= 4096 boxes, at every ring depth)
     if (ceil_div(max_seg_elems, 64) <= kSweepSmallMaxWords) {
         k_nms_sweep_small<<<G, kSweepThreads, 0, stream>>>(s, mask, keepbits, max_keep);

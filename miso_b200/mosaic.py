@@ -393,6 +393,32 @@ class MosaicPlan:
         return self.crops.results()
 
 
+def bind_host_near_gpu(device) -> Dict[str, object]:
+    """Restrict this process to the CPUs NVML reports as local to `device` (its NUMA node), so that the pinned host
+    buffers allocated afterwards — and the threads that fill them — sit on the socket whose PCIe root the GPU hangs
+    off. One process per GPU on a two-socket box otherwise leaves half the ranks copying across the socket link.
+    Call before allocating pinned memory. Returns what was done ({"bound": False, "why": ...} when NVML or the
+    affinity call is unavailable; never raises: placement is an optimisation, not part of the result)."""
+    import os
+    try:
+        import pynvml
+        dev = torch.device(device)
+        p = torch.cuda.get_device_properties(dev)
+        pynvml.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return {"bound": False, "why": "no overlap between the GPU's CPUs and this process's allowed set"}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "pci": bus, "cpus": len(allowed), "first_cpu": allowed[0], "last_cpu": allowed[-1], "host_cpus": ncpu}
+    except Exception as e:                                       # noqa: BLE001 — diagnostics only
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"[:160]}
+
+
 class HostMosaicRunner:
     """Host-facing driver of a MosaicPlan: every batch's head outputs arrive in (pinned) host memory and are copied
     to the device on a copy-in stream while earlier batches compute; the rank's results (annotation bounds, crop

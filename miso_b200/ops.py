@@ -440,7 +440,7 @@ class MultiScaleRoIAlign(torch.nn.Module):
     def __init__(self, featmap_names: List[str], output_size, sampling_ratio: int, *, canonical_scale: int = 224,
                  canonical_level: int = 4, exact: bool = True, force_gather: bool = False):
         super().__init__()
-        self.force_gather = bool(force_gather)
+        self.force_gather = force_gather
         self.featmap_names = list(featmap_names)
         self.output_size = _pair(output_size)
         self.sampling_ratio = int(sampling_ratio)

@@ -83,8 +83,12 @@ def test_tma_multiscale_many_rois_per_cta(ops):
     boxes = [cases.stress_rois(rng, 2000, hw, side=(8.0, 700.0)) for _ in range(n)]
     x = {str(i): cu(f).contiguous(memory_format=torch.channels_last) for i, f in enumerate(feats)}
     tb = [cu(b) for b in boxes]
+    from miso_b200 import _lib
+    n0 = _lib.load().mb_roi_align_tma_launches()
     a, la = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, force_gather="tma")(x, tb, [hw] * n, return_levels=True)
+    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1                      # the module passes the route through
     b, lb = ops.MultiScaleRoIAlign(["0", "1", "2", "3"], 7, 2, force_gather="gather")(x, tb, [hw] * n, return_levels=True)
+    assert _lib.load().mb_roi_align_tma_launches() == n0 + 1
     assert torch.equal(la, lb) and set(la.cpu().tolist()) == {0, 1, 2, 3}
     assert torch.equal(a, b)
     pick = np.sort(rng.choice(4000, 80, replace=False))

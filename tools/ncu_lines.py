@@ -8,6 +8,8 @@ import sys
 from collections import defaultdict
 
 rep, cubin, mangled = sys.argv[1], sys.argv[2], sys.argv[3]
+kfilter = ["-k", sys.argv[4]] if len(sys.argv) > 4 else []
+by_samples = len(sys.argv) > 5
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # instruction index -> source line, for the function
 in_fn, line_of, cur = False, [], None
@@ -23,7 +25,7 @@ for ln in dis:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
         line_of.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + kfilter, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ie, ss = hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -35,5 +37,5 @@ for i, r in enumerate(sass):
     agg[key] += int(r[ie]); samp[key] += int(r[ss])
 tot = sum(agg.values()); ts = sum(samp.values())
 print(f"total warp-instructions {tot}  samples {ts}")
-for key, v in sorted(agg.items(), key=lambda kv: -kv[1])[:45]:
+for key, v in sorted(agg.items(), key=lambda kv: (-samp[kv[0]] if by_samples else -kv[1]))[:45]:
     print(f"{str(key):32s} inst {v:12d} {100*v/tot:5.1f}%   samples {100*samp[key]/max(ts,1):5.1f}%")

@@ -214,16 +214,20 @@ def test_filter_and_crop_bit_exact(det, golden_dir, tag, ch):
     assert np.array_equal(np.concatenate([c[3].reshape(-1) for c in big.to_host(ch) if c[0] == 1]), g["pixels"])
 
 
-def test_crop_full_size_roundtrip(det):
-    """1024^2 RGB image, 300 detections: checksum-of-checksums against the oracle's slices."""
+@pytest.mark.parametrize("hw,ch", [((1024, 1024), 3), ((1000, 1021), 1), ((777, 1003), 4), ((640, 999), 3)])
+def test_crop_full_size_roundtrip(det, hw, ch):
+    """Full-size images (odd widths: every source / destination alignment occurs; 1, 3 and 4 channels: rows from a
+    few bytes to 1.6 KB, all three lanes-per-row variants of the copy), 300 detections incl. boxes clipped at the
+    image edges: every crop equals the oracle's slice."""
     rng = np.random.default_rng(3)
-    img = rng.integers(0, 256, (1024, 1024, 3), dtype=np.uint8)
-    boxes = cases.stress_rois(rng, 300, (1024, 1024), side=(8.0, 400.0))
+    img = rng.integers(0, 256, (hw[0], hw[1], ch), dtype=np.uint8)
+    boxes = cases.stress_rois(rng, 300, hw, side=(2.0, 400.0))
+    boxes[:8, 0] = 0.0; boxes[8:16, 2] = hw[1]; boxes[16:24, 3] = hw[0]; boxes[24:28] = [0, 0, hw[1], 3]
     scores = rng.uniform(0.3, 1.0, 300).astype(np.float32)
     counts = torch.tensor([300], dtype=torch.int32, device=DEV)
     out = det.filter_and_crop([cu(img)], cu(boxes[None]), cu(scores[None]), counts, 0.5)
-    crops = out.to_host(3)
-    _, _, _, _, ci, ref = M.filter_and_crop(img, boxes, scores, np.ones(300, np.int64), 0.5)
+    crops = out.to_host(ch)
+    _, _, _, _, ci, ref = M.filter_and_crop(img if ch > 1 else img[:, :, 0], boxes, scores, np.ones(300, np.int64), 0.5)
     assert len(crops) == len(ref)
     for (n, i, xywh, arr), r in zip(crops, ref):
         assert arr.shape == r.shape and np.array_equal(arr, r)
@@ -251,12 +255,13 @@ def test_dense_seam_nms_and_pack_match_the_cpu_restatement(det):
     assert torch.equal(seam.finish()[3], rows)
 
 
-def test_filter_and_crop_many_slots_multi_round(det):
-    """24 images x 200 slots = 4800 detection slots: more than one 4096-entry round of the plan kernel;
-    every image's crops must equal the oracle's, in order, with ragged counts and scores on both sides of
-    the threshold."""
+@pytest.mark.parametrize("n,cap", [(24, 200), (60, 520)])
+def test_filter_and_crop_many_slots_multi_round(det, n, cap):
+    """24 images x 200 slots = 4800 detection slots: more than one 4096-entry round of the one-CTA plan kernel;
+    60 x 520 = 31 200 slots: the chunked plan kernel (8 CTAs chained by their aggregates). Every image's crops must
+    equal the oracle's, in order, with ragged counts and scores on both sides of the threshold."""
     rng = np.random.default_rng(17)
-    n, cap, hw = 24, 200, (96, 128)
+    hw = (96, 128)
     imgs = [rng.integers(0, 256, (hw[0], hw[1], 3), dtype=np.uint8) for _ in range(n)]
     db = np.zeros((n, cap, 4), np.float32); ds = np.zeros((n, cap), np.float32)
     cnt = rng.integers(0, cap + 1, n).astype(np.int32)

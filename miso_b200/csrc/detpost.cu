@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev 
                                                                   float4* det_boxes, float4* det_boxes_net,
                                                                   float* det_scores, long long* det_labels,
                                                                   int* det_counts, int use_merge, int smem_keys) {
-    extern __shared__ unsigned long long keys_smem[];
+    extern __shared__ __align__(16) unsigned long long keys_smem[];
     unsigned long long* keys = keys_smem;
     __shared__ int s_cnt;
     __shared__ int run_off[kDetMergeMaxRuns + 1];

@@ -282,65 +282,107 @@ static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restric
                                                  const float* __restrict__ seg_offset, int full) {
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
-    __shared__ int sh_g, sh_r, sh_c;
+    // per-segment metadata of up to kMaskSegCache segments staged once per CTA: the tile -> (segment, row block, column
+    // block) lookup then costs no dependent global loads (it used to be a five-deep chain of them per tile)
+    constexpr int kMaskSegCache = 256;
+    __shared__ long long s_pre[kMaskSegCache + 1];
+    __shared__ long long s_moff[kMaskSegCache];
+    __shared__ int s_cnt[kMaskSegCache], s_st[kMaskSegCache];
+    __shared__ float s_off[kMaskSegCache];
     const int tid = threadIdx.x;
     if (s.totals[2] != 0) return;  // mask workspace too small: host retries with totals[1] words
     const long long total = s.totals[0];
+    const bool cached = G <= kMaskSegCache;
+    if (cached) {
+        for (int i = tid; i <= G; i += blockDim.x) {
+            s_pre[i] = s.tile_pre[i];
+            if (i < G) {
+                s_moff[i] = s.mask_off[i]; s_cnt[i] = s.seg_count[i]; s_st[i] = s.seg_start[i];
+                s_off[i] = seg_offset != nullptr ? seg_offset[i] : 0.0f;
+            }
+        }
+    }
+    __syncthreads();
     for (long long t = blockIdx.x; t < total; t += gridDim.x) {
-        if (tid == 0) {
+        // lane 0 of every warp decodes the tile (segment by binary search in the staged prefix, row block by the
+        // inverse of the triangular count: float estimate, exact integer correction) and broadcasts it: no barrier,
+        // and the other 31 lanes do not spend issue slots on it
+        int g = 0, r = 0, c = 0;
+        if ((tid & 31) == 0) {
             int lo = 0, hi = G;  // largest g with tile_pre[g] <= t
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (s.tile_pre[mid] <= t) lo = mid; else hi = mid;
+                if ((cached ? s_pre[mid] : s.tile_pre[mid]) <= t) lo = mid; else hi = mid;
             }
-            const long long tl = t - s.tile_pre[lo];
-            const long long T = s.seg_words[lo];
-            const double d = (double)(2 * T + 1);
-            long long r = (long long)((d - sqrt(d * d - 8.0 * (double)tl)) * 0.5);
-            if (r < 0) r = 0;
-            if (r > T - 1) r = T - 1;
-            while (r + 1 <= T - 1 && (r + 1) * T - (r + 1) * r / 2 <= tl) ++r;
-            while (r > 0 && r * T - r * (r - 1) / 2 > tl) --r;
-            sh_g = lo; sh_r = (int)r; sh_c = (int)(r + (tl - (r * T - r * (r - 1) / 2)));
+            g = lo;
+            const long long TT = ((cached ? s_cnt[g] : s.seg_count[g]) + 63) >> 6;
+            const long long tl = t - (cached ? s_pre[g] : s.tile_pre[g]);
+            long long rr;
+            if (TT <= 2048) {
+                const float d = (float)(2 * TT + 1);
+                rr = (long long)((d - sqrtf(fmaxf(d * d - 8.0f * (float)tl, 0.0f))) * 0.5f);
+            } else {
+                const double d = (double)(2 * TT + 1);
+                rr = (long long)((d - sqrt(d * d - 8.0 * (double)tl)) * 0.5);
+            }
+            if (rr < 0) rr = 0;
+            if (rr > TT - 1) rr = TT - 1;
+            while (rr + 1 <= TT - 1 && (rr + 1) * TT - (rr + 1) * rr / 2 <= tl) ++rr;
+            while (rr > 0 && rr * TT - rr * (rr - 1) / 2 > tl) --rr;
+            r = (int)rr; c = (int)(rr + (tl - (rr * TT - rr * (rr - 1) / 2)));
         }
-        __syncthreads();
-        const int g = sh_g, r = sh_r, c = sh_c;
-        const int n = s.seg_count[g], T = s.seg_words[g], st = s.seg_start[g];
+        g = __shfl_sync(0xffffffffu, g, 0); r = __shfl_sync(0xffffffffu, r, 0); c = __shfl_sync(0xffffffffu, c, 0);
+        const int n = cached ? s_cnt[g] : s.seg_count[g];
+        const int st = cached ? s_st[g] : s.seg_start[g];
+        const long long moff = cached ? s_moff[g] : s.mask_off[g];
+        const float off = cached ? s_off[g] : (seg_offset != nullptr ? seg_offset[g] : 0.0f);
+        const int T = (n + 63) >> 6;
         const int ncol = min(64, n - c * 64);
-        const float off = seg_offset != nullptr ? seg_offset[g] : 0.0f;
+        // two threads per row: thread (row, half) tests columns 32*half .. 32*half+31 and writes its own
+        // 32-bit half of the mask word (little-endian halves of the 64-bit word)
+        const int row = r * 64 + (tid & 63), half = tid >> 6;
+        float4 a_raw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < n) a_raw = sbox[st + row];                 // issued together with the column box load below
         if (tid < ncol) {
             const float4 b = offset_box(sbox[st + c * 64 + tid], off);
             cbox[tid] = b;
             carea[tid] = box_area_rn(b);
         }
         __syncthreads();
-        // two threads per row: thread (row, half) tests columns 32*half .. 32*half+31 and writes its own
-        // 32-bit half of the mask word (little-endian halves of the 64-bit word)
-        const int row = r * 64 + (tid & 63), half = tid >> 6;
         unsigned int word = 0;
         if (row < n) {
-            const float4 a = offset_box(sbox[st + row], off);
+            const float4 a = offset_box(a_raw, off);
             const float area_a = box_area_rn(a);
             // Diagonal tiles carry the full symmetric word (bits j < row too): the sweep resolves a
             // 64-box block in parallel from "who suppresses me" = word & lower bits.
             const int skip = (r == c) ? (tid & 63) : -1;
             const int j0 = 32 * half, j1 = min(ncol, j0 + 32);
             if (thr_up > 0.0f) {
-                // an IoU above a positive threshold needs a positive intersection: most pairs are
-                // disjoint and never reach the division
+                // An IoU above a positive threshold needs a positive intersection, and most pairs are disjoint. Pass 1
+                // marks the columns whose box overlaps this row's at all (four chained compares, no divergence: a
+                // superset of "positive intersection" — degenerate boxes that slip through get IoU 0 or NaN below);
+                // pass 2 runs the exact IoU only on those, each lane walking its own few set bits. With one loop a
+                // warp paid for the division whenever ANY of its 32 rows overlapped the column.
+                unsigned int cand = 0;
+#pragma unroll 8
                 for (int j = j0; j < j1; ++j) {
                     const float4 b = cbox[j];
-                    const float xx1 = (a.x < b.x) ? b.x : a.x, yy1 = (a.y < b.y) ? b.y : a.y;
-                    const float xx2 = (b.z < a.z) ? b.z : a.z, yy2 = (b.w < a.w) ? b.w : a.w;
-                    if (xx2 > xx1 && yy2 > yy1 && j != skip &&
-                        iou_suppresses(a, area_a, b, carea[j], thr_up))
-                        word |= 1u << (j - j0);
+                    if (b.x < a.z && a.x < b.z && b.y < a.w && a.y < b.w) cand |= 1u << (j - j0);
+                }
+                if (skip >= j0 && skip < j0 + 32) cand &= ~(1u << (skip - j0));
+                while (cand) {
+                    const int q = __ffs((int)cand) - 1;
+                    cand &= cand - 1u;
+                    if (iou_suppresses(a, area_a, cbox[j0 + q], carea[j0 + q], thr_up)) word |= 1u << q;
                 }
             } else {
                 for (int j = j0; j < j1; ++j)
                     if (j != skip && iou_suppresses(a, area_a, cbox[j], carea[j], thr_up)) word |= 1u << (j - j0);
             }
-            reinterpret_cast<unsigned int*>(mask)[2 * (s.mask_off[g] + (long long)row * T + c) + half] = word;
+            // full mode (fixed-point sweep): word-major [T][n], so that the sweep's thread-per-box loads and the stores
+            // here are contiguous across boxes; otherwise row-major [n][T] for the block sweeps
+            const long long at = full ? (long long)c * n + row : (long long)row * T + c;
+            reinterpret_cast<unsigned int*>(mask)[2 * (moff + at) + half] = word;
         }
         if (full && r != c) {
             // the fixed-point sweep reads "who suppresses me" for whole rows: IoU is symmetric, so the tile's transpose
@@ -354,7 +396,7 @@ static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restric
                 if (lane == j) tw = b;
             }
             const int trow = c * 64 + 32 * half + lane;
-            if (trow < n) reinterpret_cast<unsigned int*>(mask)[2 * (s.mask_off[g] + (long long)trow * T + r) + sub] = tw;
+            if (trow < n) reinterpret_cast<unsigned int*>(mask)[2 * (moff + (long long)r * n + trow) + sub] = tw;
         }
         __syncthreads();
     }
@@ -656,12 +698,12 @@ static __global__ void __launch_bounds__(kFixThreads) k_nms_fixpoint(SegArrays s
     const int n = s.seg_count[g];
     const int T = s.seg_words[g];
     if (n == 0 || s.totals[2] != 0) { if (t == 0) s.seg_kept[g] = 0; return; }
-    const unsigned long long* m = mask + s.mask_off[g] + (long long)t * T;
+    const unsigned long long* m = mask + s.mask_off[g] + t;      // word-major mask: word w of box t at m[w * n]
     unsigned long long* kb = keepbits + s.keep_off[g];
     const int nw = min((warp >> 1) + 1, T);                 // words holding boxes before this warp's (warp-uniform)
     unsigned long long S[kFixWords];
 #pragma unroll
-    for (int w = 0; w < kFixWords; ++w) S[w] = (w < nw && t < n) ? m[w] : 0ull;
+    for (int w = 0; w < kFixWords; ++w) S[w] = (w < nw && t < n) ? m[(long long)w * n] : 0ull;
 #pragma unroll
     for (int w = 0; w < kFixWords; ++w)
         if (w == (t >> 6)) S[w] &= (1ull << (t & 63)) - 1ull;

@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_hist(const RpnDev d, RpnScr
 }
 
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnScratch w, long long* topk_idx_out) {
-    extern __shared__ unsigned long long keys[];  // [kSelectSortCap]
-    __shared__ int s_last, s_need, s_prefix_ok;
+    extern __shared__ __align__(16) unsigned long long keys[];  // [kSelectSortCap]
+    __shared__ int s_last, s_need, s_prefix_ok, s_single;
     __shared__ unsigned long long s_thr;
     __shared__ int hist256[256];
     int n, l, chunk;
@@ -163,17 +163,52 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
     unsigned long long* sel = w.sel + (size_t)n * Ktot + d.koff[l];
     unsigned long long* cand = w.cand + (size_t)n * sumA + d.aoff[l];
     const int end = min(d.AL[l], (chunk + 1) * kRpnChunk);
-    for (int m0 = chunk * kRpnChunk; m0 < end; m0 += kRpnThreads) {   // warp-uniform trip count
-        const int m = m0 + tid;
-        unsigned int key = 0xffffffffu;
-        if (m < end) key = desc_score_key(__ldg(obj + m));
-        const int bin = (m < end) ? (int)(key >> 20) : kHistBins;
-        const unsigned long long ck =
-            ((unsigned long long)key << 32) | (unsigned int)(m < end ? ref_index_from_mem(m, d.A[l], HW) : 0);
-        const int s1 = warp_alloc_slot(&w.n_sel[g], bin < tb);
-        if (bin < tb) sel[s1] = ck;
-        const int s2 = warp_alloc_slot(&w.n_cand[g], bin == tb);
-        if (bin == tb) cand[s2] = ck;
+    // this CTA's logits: all loads first (one latency), the definite winners (bin < threshold bin) and the threshold-bin
+    // candidates counted per thread, one block scan, ONE global atomic per list for the whole CTA, then the writes
+    // (the order inside the lists is irrelevant: keys are unique and sorted / selected below)
+    constexpr int kPer = kRpnChunk / kRpnThreads;
+    unsigned int key[kPer];
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int m = chunk * kRpnChunk + q * kRpnThreads + tid;
+        key[q] = m < end ? desc_score_key(__ldg(obj + m)) : 0xffffffffu;
+    }
+    int nsel = 0, ncnd = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+        const int m = chunk * kRpnChunk + q * kRpnThreads + tid;
+        const int bin = m < end ? (int)(key[q] >> 20) : kHistBins;
+        nsel += bin < tb; ncnd += bin == tb;
+    }
+    {
+        __shared__ int s_wsel[32], s_wcnd[32], s_bsel, s_bcnd;
+        const int lane = tid & 31, wid = tid >> 5;
+        int xs = nsel, xc = ncnd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ys = __shfl_up_sync(0xffffffffu, xs, o), yc = __shfl_up_sync(0xffffffffu, xc, o);
+            if (lane >= o) { xs += ys; xc += yc; }
+        }
+        if (lane == 31) { s_wsel[wid] = xs; s_wcnd[wid] = xc; }
+        __syncthreads();
+        int ps = 0, pc = 0, ts = 0, tc = 0;
+        for (int q = 0; q < kRpnThreads / 32; ++q) {
+            ps += q < wid ? s_wsel[q] : 0; ts += s_wsel[q];
+            pc += q < wid ? s_wcnd[q] : 0; tc += s_wcnd[q];
+        }
+        if (tid == 0) s_bsel = ts ? atomicAdd(&w.n_sel[g], ts) : 0;
+        if (tid == 32) s_bcnd = tc ? atomicAdd(&w.n_cand[g], tc) : 0;
+        __syncthreads();
+        int js = s_bsel + ps + xs - nsel, jc = s_bcnd + pc + xc - ncnd;
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {
+            const int m = chunk * kRpnChunk + q * kRpnThreads + tid;
+            if (m >= end) continue;
+            const int bin = (int)(key[q] >> 20);
+            const unsigned long long ck = ((unsigned long long)key[q] << 32) | (unsigned int)ref_index_from_mem(m, d.A[l], HW);
+            if (bin < tb) sel[js++] = ck;
+            else if (bin == tb) cand[jc++] = ck;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -189,6 +224,13 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
     unsigned long long prefix = 0x000fffffffffffffull;   // take every candidate unless narrowed below
     // (sorting all candidates together with the definite picks instead of narrowing first measured slower: the
     // bitonic sort doubles in size, the seven radix passes over a few hundred keys are cheap)
+    // the candidates are read many times below: once from global memory into the upper half of the key buffer
+    unsigned long long* scand = keys + kSelectSortCap / 2;
+    const bool staged = nc <= kSelectSortCap / 2;
+    if (staged) {
+        for (int i = tid; i < nc; i += kRpnThreads) scand[i] = __ldcg(&cand[i]);
+        __syncthreads();
+    }
     if (nc > need) {
         // radix-select the need-th smallest candidate key over the remaining 52 bits, 8 bits per pass
         unsigned long long pmask = 0;
@@ -199,7 +241,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
             for (int i = tid; i < 256; i += kRpnThreads) hist256[i] = 0;
             __syncthreads();
             for (int i = tid; i < nc; i += kRpnThreads) {
-                const unsigned long long ck = __ldcg(&cand[i]) & 0x000fffffffffffffull;
+                const unsigned long long ck = (staged ? scand[i] : __ldcg(&cand[i])) & 0x000fffffffffffffull;
                 if ((ck & pmask) == prefix) atomicAdd(&hist256[(int)((ck >> sft) & ((1u << bits) - 1))], 1);
             }
             __syncthreads();
@@ -216,6 +258,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
                     if (cum < need && cum + loc[q] >= need) {
                         s_need = need - cum;
                         s_thr = prefix | ((unsigned long long)(tid * 8 + q) << sft);
+                        s_single = loc[q] == 1;
                     }
                     cum += loc[q];
                 }
@@ -224,7 +267,19 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
             need = s_need;
             prefix = s_thr;
             pmask |= ((unsigned long long)((1u << bits) - 1)) << sft;
+            const bool single = s_single != 0;
             __syncthreads();
+            if (single && sft > 0) {
+                // one candidate left under the prefix: it is the last winner; take its remaining bits directly
+                // instead of resolving them eight at a time (typical: the score bits alone separate the candidates)
+                for (int i = tid; i < nc; i += kRpnThreads) {
+                    const unsigned long long ck = (staged ? scand[i] : __ldcg(&cand[i])) & 0x000fffffffffffffull;
+                    if ((ck & pmask) == prefix) s_thr = ck;
+                }
+                __syncthreads();
+                prefix = s_thr;
+                break;
+            }
         }
         // prefix is now the exact low-52-bit value of the last winner (keys are unique)
     }
@@ -235,7 +290,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
         const int i = i0 + tid;
         unsigned long long ck = 0;
         bool win = false;
-        if (i < nc) { ck = __ldcg(&cand[i]); win = (ck & 0x000fffffffffffffull) <= prefix; }
+        if (i < nc) { ck = staged ? scand[i] : __ldcg(&cand[i]); win = (ck & 0x000fffffffffffffull) <= prefix; }
         const int slot = warp_alloc_slot(&s_prefix_ok, win);
         if (win) keys[na + slot] = ck;
     }

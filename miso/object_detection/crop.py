@@ -14,6 +14,16 @@ import torch
 from miso.object_detection.dataset.project import Project
 
 
+def _imread(path: str) -> np.ndarray:
+    """Pixels as skimage.io.imread returns them (its default plugin reads through PIL): palette images expanded to
+    RGB / RGBA, everything else in its stored dtype and channel count."""
+    from PIL import Image
+    with Image.open(path) as img:
+        if img.mode == "P":
+            img = img.convert("RGBA" if "transparency" in img.info else "RGB")
+        return np.array(img)                       # copy: PIL-backed arrays are read-only
+
+
 def crop_objects(project: Project, output_dir: str, relative_to=None):
     from PIL import Image
     from miso_b200 import detection
@@ -28,14 +38,26 @@ def crop_objects(project: Project, output_dir: str, relative_to=None):
     for image in project.image_dict.values():
         if len(image.boxes) == 0:
             continue
-        im = np.asarray(Image.open(image.full_path))
-        dev = torch.from_numpy(np.array(im, copy=True)).cuda()       # copy: PIL-backed arrays are read-only
+        im = _imread(image.full_path)
+        # The gather moves bytes: any dtype goes through as [H, W, bytes per pixel] and is viewed back afterwards
+        # (16-bit TIFFs, float images: skimage.io.imread hands those to the reference's numpy slice unchanged)
+        px_shape = im.shape[2:]
+        bpp = int(np.prod(px_shape, dtype=np.int64)) * im.dtype.itemsize
+        as_bytes = np.ascontiguousarray(im).view(np.uint8).reshape(im.shape[0], im.shape[1], bpp)
+        dev = torch.from_numpy(as_bytes).cuda()
         k = len(image.boxes)
-        bounds = torch.tensor([[float(v) for v in b.bounds] for b in image.boxes], dtype=torch.float32, device="cuda")
+        # integer corners exactly as the reference computes them (Annotation.coords_int: Python-float sums, np.round,
+        # int) — annotations parsed from XML / CVAT are float64 and x + w can round differently in fp32; integer-valued
+        # corners below 2^24 pass through the device's fp32 rounding unchanged, negative ones keep numpy's slice rules
+        corners = [box.coords_int for box in image.boxes]
+        if any(abs(v) >= (1 << 24) for c in corners for v in c):
+            raise ValueError(f"crop_objects: box corner beyond 2^24 in {image.full_path}")
+        bounds = torch.tensor(corners, dtype=torch.float32, device="cuda")
         scores = torch.ones((1, k), dtype=torch.float32, device="cuda")
         counts = torch.tensor([k], dtype=torch.int32, device="cuda")
-        out = detection.filter_and_crop([dev], bounds[None], scores, counts, 0.5, boxes_are_xywh=True)
-        crops = out.to_host(1 if im.ndim == 2 else im.shape[2])
+        out = detection.filter_and_crop([dev], bounds[None], scores, counts, 0.5, boxes_are_xywh=False)
+        crops = [(n, i, xywh, np.ascontiguousarray(c).reshape(c.shape[0], c.shape[1], bpp).view(im.dtype).reshape(c.shape[:2] + px_shape))
+                 for n, i, xywh, c in out.to_host(bpp)]
         path = Path(image.full_path)
         for (_, idx, _xywh, crop), box in zip(crops, image.boxes):
             if relative_to is not None:

@@ -80,7 +80,7 @@ __global__ void k_grid_anchors(BaseAnchors ba, int num_base, int gh, int gw, int
     }
 }
 
-static inline int grid_for(long long n) { return (int)min((long long)kNumSMs * 16, max(1ll, ceil_div64(n, 256))); }
+static inline int grid_for(long long n) { return (int)min((long long)num_sms() * 16, max(1ll, ceil_div64(n, 256))); }
 
 }  // namespace mb
 

@@ -17,9 +17,34 @@
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory: the attribute is per device and sticky, so it is only set when a
+// call site needs more than it has already asked for on that device (not on every launch).
+#define MB_DYN_SMEM(kernel, bytes)                                                                        \
+    do {                                                                                                  \
+        static int have__[64] = {};                                                                       \
+        int dev__ = 0;                                                                                    \
+        MB_CUDA(cudaGetDevice(&dev__));                                                                   \
+        const int want__ = (int)(bytes);                                                                  \
+        if (want__ > have__[dev__ & 63]) {                                                                \
+            MB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want__));   \
+            have__[dev__ & 63] = want__;                                                                  \
+        }                                                                                                 \
+    } while (0)
+
 namespace mb {
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (148 on a B200), asked once per device: grids are sized in multiples of it
+inline int num_sms() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int v = cached[dev];
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached[dev] = v;                 // racing first calls store the same value
+    }
+    return v;
+}
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

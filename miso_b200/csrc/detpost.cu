@@ -327,7 +327,7 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     int cap = use_merge ? 2 * bound : next_pow2(bound > 2 ? bound : 2);   // merge keeps source + merged order
     if (cap > kDetSortCap) cap = kDetSortCap;                             // larger actual counts sort in w.gkeys
     const int smem = (cap > 2 ? cap : 2) * (int)sizeof(unsigned long long);
-    MB_CUDA(cudaFuncSetAttribute(k_det_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    MB_DYN_SMEM(k_det_finalize, smem);
     k_det_finalize<<<d.N, kDetFinalThreads, smem, stream>>>(d, im, w, (float4*)det_boxes, (float4*)det_boxes_net, det_scores,
                                                            (long long*)det_labels, det_counts, use_merge, cap);
     MB_LAUNCH_CHECK();

@@ -208,7 +208,7 @@ extern "C" int mb_nms(const float* boxes, const float* scores, const int64_t* gr
     MB_CUDA(cudaMemsetAsync(workspace, 0, c.off, stream));
     MB_CUDA(cudaMemsetAsync(w.bseg, 0xff, sizeof(int) * K, stream));
     MB_CUDA(cudaMemsetAsync(w.kseg, 0xff, sizeof(int) * K, stream));
-    const int grid = (int)min((long long)kNumSMs * 8, ceil_div64(K, 256));
+    const int grid = (int)min((long long)num_sms() * 8, ceil_div64(K, 256));
     if (mode == MB_NMS_TRICK) {
         k_box_max<<<grid, 256, 0, stream>>>(boxes, K * 4, w.scalars);
         MB_LAUNCH_CHECK();

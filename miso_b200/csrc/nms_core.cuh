@@ -769,7 +769,7 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
                                  cudaStream_t stream, const float* seg_offset = nullptr) {
     const float thr_up = strict_gt_threshold(iou_threshold);
     const bool fix = max_seg_elems <= kFixThreads && !sweep_in_order();
-    k_nms_mask<<<kNumSMs * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset, fix ? 1 : 0);
+    k_nms_mask<<<num_sms() * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset, fix ? 1 : 0);
     MB_LAUNCH_CHECK();
     if (fix) {
         k_nms_fixpoint<<<G, kFixThreads, 0, stream>>>(s, mask, keepbits, max_keep);
@@ -788,7 +788,7 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
         while (nbuf > 1 && ((long long)Tcap + 64ll * nbuf * Tcap) * 8 > 200 * 1024) --nbuf;
         const long long bytes = ((long long)Tcap + 64ll * nbuf * Tcap) * 8;
         if (bytes <= 200 * 1024) {
-            MB_CUDA(cudaFuncSetAttribute(k_nms_sweep_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            MB_DYN_SMEM(k_nms_sweep_wide, (int)bytes);
             k_nms_sweep_wide<<<G, kSweepThreads, (int)bytes, stream>>>(s, mask, keepbits, max_keep, Tcap, nbuf);
             MB_LAUNCH_CHECK();
             return MB_OK;
@@ -797,7 +797,7 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
     const int smem = sweep_smem_bytes(ceil_div(max_seg_elems, 64) + 1);
     if (smem > 48 * 1024) {
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
-        MB_CUDA(cudaFuncSetAttribute(k_nms_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MB_DYN_SMEM(k_nms_sweep, smem);
     }
     k_nms_sweep<<<G, kSweepBigThreads, smem, stream>>>(s, mask, keepbits, max_keep);
     MB_LAUNCH_CHECK();

@@ -127,7 +127,7 @@ extern "C" int mb_mask_prob(const float* mask_logits, const int64_t* labels, int
     if (!mask_logits || !labels || !out) return MB_ERR_INVALID_ARG;
     const int plane = mask_side * mask_side;
     const long long total = num_masks * (long long)plane;
-    const int grid = (int)min((long long)mb::kNumSMs * 8, (total + 255) / 256);
+    const int grid = (int)min((long long)mb::num_sms() * 8, (total + 255) / 256);
     mb::k_mask_prob<<<grid, 256, 0, (cudaStream_t)stream>>>(mask_logits, (const long long*)labels, num_classes, plane, total, out);
     MB_LAUNCH_CHECK();
     return MB_OK;

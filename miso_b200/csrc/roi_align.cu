@@ -985,7 +985,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             static const int occ_env = getenv("MB_ROI_OCC") ? atoi(getenv("MB_ROI_OCC")) : 0;      // development switch
 #define MB_NHWC4D(E, O)                                                                                              \
     do {                                                                                                            \
-        MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc4d<E, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemd)); \
+        MB_DYN_SMEM((k_roi_align_nhwc4d<E, O>), smemd); \
         k_roi_align_nhwc4d<E, O><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows, ones);        \
     } while (0)
             if (p.exact) { if (occ_env == 3) MB_NHWC4D(true, 3); else MB_NHWC4D(true, 4); }
@@ -997,10 +997,10 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const int obuf = (kChunk * opitch + 3) & ~3;
         const int smem = 2 * obuf * (int)sizeof(float) + nbins * 4 * 32;
         if (p.exact) {
-            MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_DYN_SMEM(k_roi_align_nhwc<true>, smem);
             k_roi_align_nhwc<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out);
         } else {
-            MB_CUDA(cudaFuncSetAttribute(k_roi_align_nhwc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_DYN_SMEM(k_roi_align_nhwc<false>, smem);
             k_roi_align_nhwc<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out);
         }
         MB_LAUNCH_CHECK();
@@ -1013,10 +1013,10 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const int smem = (kChunk * opitch + patch_floats) * (int)sizeof(float) + nbins * 4 * 32;
         if (smem > 200 * 1024) return MB_ERR_UNSUPPORTED;
         if (p.exact) {
-            MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_DYN_SMEM(k_roi_align_sr2<true>, smem);
             k_roi_align_sr2<true><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats, variant);
         } else {
-            MB_CUDA(cudaFuncSetAttribute(k_roi_align_sr2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_DYN_SMEM(k_roi_align_sr2<false>, smem);
             k_roi_align_sr2<false><<<(int)num_rois, kRoiThreads, smem, stream>>>(p, rois, out, levels_out, patch_floats, variant);
         }
         MB_LAUNCH_CHECK();
@@ -1031,7 +1031,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         const int grid = (int)(num_rois * chunks);
 #define MB_ROI_LAUNCH(E, S)                                                                                  \
     do {                                                                                                    \
-        MB_CUDA(cudaFuncSetAttribute(k_roi_align_staged<E, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        MB_DYN_SMEM((k_roi_align_staged<E, S>), smem); \
         k_roi_align_staged<E, S><<<grid, kRoiThreads, smem, stream>>>(p, rois, (int)num_rois, out, levels_out, stage_floats); \
     } while (0)
         const bool sr2 = p.sampling_ratio == 2;
@@ -1042,7 +1042,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
         return MB_OK;
     }
     const long long total = num_rois * (long long)p.channels * nbins;
-    const int grid = (int)min((long long)kNumSMs * 32, ceil_div64(total, 256));
+    const int grid = (int)min((long long)num_sms() * 32, ceil_div64(total, 256));
     k_roi_align_direct<<<grid, 256, 0, stream>>>(p, rois, total, out, levels_out);
     MB_LAUNCH_CHECK();
     return MB_OK;

@@ -493,7 +493,7 @@ extern "C" int mb_rpn_proposals(const mb_rpn_params* p, float* proposals_out, fl
     k_rpn_hist<<<stream_blocks, kRpnThreads, 0, stream>>>(d, w);
     MB_LAUNCH_CHECK();
     const int sel_smem = kSelectSortCap * (int)sizeof(unsigned long long);
-    MB_CUDA(cudaFuncSetAttribute(k_rpn_select, cudaFuncAttributeMaxDynamicSharedMemorySize, sel_smem));
+    MB_DYN_SMEM(k_rpn_select, sel_smem);
     k_rpn_select<<<stream_blocks, kRpnThreads, sel_smem, stream>>>(d, w, (long long*)topk_idx_out);
     MB_LAUNCH_CHECK();
     k_rpn_decode<<<G, kRpnThreads, 0, stream>>>(d, im, w);
@@ -508,7 +508,7 @@ extern "C" int mb_rpn_proposals(const mb_rpn_params* p, float* proposals_out, fl
     if (rc != MB_OK) return rc;
     const int cap = next_pow2(d.koff[d.L] > 2 ? d.koff[d.L] : 2);
     const int fin_smem = cap * (int)sizeof(unsigned long long);
-    MB_CUDA(cudaFuncSetAttribute(k_rpn_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, fin_smem));
+    MB_DYN_SMEM(k_rpn_finalize, fin_smem);
     k_rpn_finalize<<<d.N, kRpnThreads, fin_smem, stream>>>(d, w, (float4*)proposals_out, scores_out, counts_out, cap);
     MB_LAUNCH_CHECK();
     return MB_OK;

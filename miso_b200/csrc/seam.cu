@@ -439,7 +439,7 @@ extern "C" int mb_seam_nms(const float* block, int64_t rows, int32_t rows_per_ti
     const int pair_smem = kSeamChunk * (int)sizeof(SeamCand);
     static bool attr = false;
     if (!attr) {
-        MB_CUDA(cudaFuncSetAttribute(k_seam_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem));
+        MB_DYN_SMEM(k_seam_pairs, pair_smem);
         attr = true;
     }
     k_seam_pairs<<<tiles, threads, pair_smem, stream>>>(block, (int)rows, rows_per_tile, tiles, thr_up, w, (int)edge_capacity);

@@ -239,7 +239,7 @@ extern "C" int mb_box_iou(const float* boxes1, int64_t n1, const float* boxes2, 
     if (n1 == 0 || n2 == 0) return MB_OK;
     if (!boxes1 || !boxes2 || !iou_out) return MB_ERR_INVALID_ARG;
     const long long total = n1 * n2;
-    const int grid = (int)min((long long)kNumSMs * 16, ceil_div64(total, 256));
+    const int grid = (int)min((long long)num_sms() * 16, ceil_div64(total, 256));
     k_box_iou<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)boxes1, (int)n1, (const float4*)boxes2, (int)n2, iou_out);
     MB_LAUNCH_CHECK();
     return MB_OK;
@@ -297,7 +297,7 @@ extern "C" int mb_roi_align_backward(const float* grad, const float* rois, int64
     const int smem = patch_floats * (int)sizeof(float);
     static bool attr = false;
     if (!attr) {
-        MB_CUDA(cudaFuncSetAttribute(k_roi_align_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MB_DYN_SMEM(k_roi_align_backward, smem);
         attr = true;
     }
     k_roi_align_backward<<<(unsigned)(num_rois * chunks), kBwdThreads, smem, stream>>>(

@@ -332,3 +332,52 @@ def test_patched_model_runs_channels_last_and_never_syncs_before_the_results():
     assert seen["nhwc"] and seen["lazy"]
     assert not seen["props"].materialised                      # the whole forward ran without reading the proposal counts
     assert len(out) == 2 and out[0]["boxes"].shape[1] == 4
+
+
+def test_crop_objects_any_dtype_palette_and_float64_bounds(tmp_path):
+    """crop_objects on what skimage.io.imread hands the reference: a 16-bit TIFF (cropped as bytes and viewed back),
+    a palette PNG (expanded to RGB), an RGB PNG — with float64 annotation bounds whose x + w lands on .5 only in
+    float64, a negative corner (numpy's wrap-around slice) and a box past the image edge. Every written crop equals
+    the reference's `im[c[1]:c[3], c[0]:c[2], ...]` with c = int(np.round(.)) of the Python-float sums."""
+    from PIL import Image
+    from miso.object_detection.crop import crop_objects
+    from miso.object_detection.dataset.annotation import RectangleAnnotation
+    from miso.object_detection.dataset.image import ImageMetadata
+    from miso.object_detection.dataset.project import Project
+    rng = np.random.default_rng(5)
+    idir = tmp_path / "in"
+    idir.mkdir()
+    im16 = rng.integers(0, 65536, (90, 130), dtype=np.uint16)
+    Image.fromarray(im16).save(idir / "deep.tif")
+    pal = Image.fromarray(rng.integers(0, 256, (70, 95), dtype=np.uint8), mode="P")
+    pal.putpalette([int(v) for v in rng.integers(0, 256, 768)])
+    pal.save(idir / "pal.png")
+    rgb = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    Image.fromarray(rgb).save(idir / "rgb.png")
+    want = {"deep.tif": im16, "pal.png": np.array(pal.convert("RGB")), "rgb.png": rgb}
+    # 56.828.. + 17.671.. = 74.50000016 in float64 (-> 75) but 74.5 in float32 (-> 74, half to even); the second box
+    # is 29.4999981 in float64 (-> 29) and 29.5 in float32 (-> 30): XML / CVAT annotations are Python floats
+    boxes = [(56.82802170936761, 5.0, 17.671978449834047, 30.0), (12.996859387349325, 12.996859387349325, 16.50313874181763, 16.50313874181763),
+             (0.3, 0.3, 2.2, 2.2), (-4.0, 3.0, 10.0, 12.0), (50.0, 40.0, 500.0, 500.0), (3.5, 2.5, 4.0, 5.0)]
+    assert int(np.round(boxes[0][0] + boxes[0][2])) != int(np.round(np.float32(boxes[0][0]) + np.float32(boxes[0][2])))
+    project = Project()
+    for name in want:
+        meta = ImageMetadata(name, str(idir))
+        meta.boxes = [RectangleAnnotation(*b, label="obj") for b in boxes]
+        project.add_image(meta)
+    odir = tmp_path / "out"
+    crop_objects(project, str(odir))
+    seen = 0
+    for name, im in want.items():
+        stem, suffix = name.rsplit(".", 1)
+        for x, y, w, h in boxes:
+            c = tuple(int(np.round(v)) for v in (x, y, x + w, y + h))
+            ref = im[c[1]:c[3], c[0]:c[2], ...]
+            f = odir / "obj" / f"{stem}_{x:.0f}_{y:.0f}_{w:.0f}_{h:.0f}.{suffix}"
+            if ref.size == 0:
+                assert not f.exists()
+                continue
+            got = np.array(Image.open(f))
+            assert got.dtype == ref.dtype and got.shape == ref.shape and np.array_equal(got, ref), (name, (x, y, w, h))
+            seen += 1
+    assert seen >= 15

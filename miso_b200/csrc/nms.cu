@@ -102,10 +102,15 @@ __global__ void k_scatter_boxes(const float4* __restrict__ boxes, const float* _
 // kept set of a single segment -> keep_out in sweep order (already the global score order)
 __global__ void __launch_bounds__(1024) k_emit_single(SegArrays s, const unsigned long long* __restrict__ skey,
                                                      const unsigned long long* __restrict__ keepbits,
-                                                     long long* keep_out, long long* status) {
+                                                     long long* keep_out, long long* status,
+                                                     const unsigned int* __restrict__ bad_flag) {
     __shared__ long long sh[64];
     __shared__ long long carry;
     const int tid = threadIdx.x;
+    if (*bad_flag != 0u) {                 // a group index >= num_groups (vanilla mode with one group)
+        if (tid == 0) { status[0] = -2; status[1] = s.totals[1]; }
+        return;
+    }
     if (s.totals[2] != 0) {
         if (tid == 0) { status[0] = -1; status[1] = s.totals[1]; }
         return;
@@ -228,7 +233,7 @@ extern "C" int mb_nms(const float* boxes, const float* scores, const int64_t* gr
     int rc = launch_mask_and_sweep(w.sbox, w.seg, G, (int)K, iou_threshold, mask, w.keepbits, 0, stream);
     if (rc != MB_OK) return rc;
     if (G == 1) {
-        k_emit_single<<<1, 1024, 0, stream>>>(w.seg, w.skey, w.keepbits, (long long*)keep_out, (long long*)status_out);
+        k_emit_single<<<1, 1024, 0, stream>>>(w.seg, w.skey, w.keepbits, (long long*)keep_out, (long long*)status_out, w.scalars + 1);
         MB_LAUNCH_CHECK();
         return MB_OK;
     }

@@ -328,3 +328,16 @@ def test_maskrcnn_inference_selected_channel_sigmoid(ops):
     assert [tuple(g.shape) for g in got] == [tuple(r.shape) for r in ref]
     for g, r in zip(got, ref):
         assert float((g.cpu() - r).abs().max()) <= 1e-6 if r.numel() else True
+
+
+def test_nms_reports_group_index_outside_range(ops):
+    """mb_nms in per-group mode must flag a group index >= num_groups for any group count — also for a single group,
+    where the kept set is emitted by the one-segment kernel."""
+    from miso_b200 import MisoB200Error
+    rng = np.random.default_rng(2)
+    b, s = cases.random_boxes(rng, 300, extent=100.0), cases.distinct_scores(rng, 300)
+    for groups, num_groups in ((np.r_[np.zeros(299, np.int64), 1], 1), (rng.integers(0, 4, 300), 3)):
+        with pytest.raises(MisoB200Error):
+            ops._nms_impl(cu(b), cu(s), cu(groups.astype(np.int64)), num_groups, 1, 0.5)
+    ok = ops._nms_impl(cu(b), cu(s), cu(np.zeros(300, np.int64)), 1, 1, 0.5)
+    assert np.array_equal(ok.cpu().numpy(), D.nms(b, s, 0.5))

@@ -389,7 +389,7 @@ extern "C" int mb_crop_gather(const mb_crop_params* p, const int32_t* rects, con
     // finds no rows of a crop left still pays for reading its rectangle, so y only grows while x cannot fill the GPU)
     const long long slots = (long long)d.N * d.cap;
     const int gx = (int)std::min<long long>(std::max<long long>(slots, 1), (long long)num_sms() * 8);
-    const int gy = (int)std::min<long long>(16, std::max<long long>(1, ((long long)num_sms() * 64) / std::max<long long>(slots, 1)));
+    const int gy = (int)std::min<long long>(16, std::max<long long>(1, ((long long)num_sms() * 256) / std::max<long long>(slots, 1)));
     dim3 grid(gx, gy);
     k_crop_gather<<<grid, 256, 0, (cudaStream_t)stream>>>(d, (const int4*)rects, src, (const long long*)offsets,
                                                          (long long*)totals, crops_out, crops_capacity_bytes);

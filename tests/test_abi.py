@@ -41,6 +41,14 @@ def test_binding_table_matches_header(lib_path):
     assert lib.mb_abi_version() == 1
     info = lib.mb_build_info().decode()
     assert "sm_100a" in info
+    # the kernel list it reports is the set of __global__ functions in the sources
+    import glob, re
+    src = os.path.join(os.path.dirname(os.path.abspath(_lib.__file__)), "csrc")
+    kernels = set()
+    for f in glob.glob(os.path.join(src, "*.cu")) + glob.glob(os.path.join(src, "*.cuh")):
+        with open(f) as fh:
+            kernels |= set(re.findall(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s+)?(k_\w+)", fh.read()))
+    assert set(info.split("kernels=")[1].split(",")) == kernels
 
 
 def test_struct_sizes_match_c_layout(lib_path):

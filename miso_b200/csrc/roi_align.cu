@@ -646,9 +646,11 @@ __device__ __forceinline__ float4 bin_dedup(const char* __restrict__ gp, const u
         const int iy = smp >> 1, ix = smp & 1;
         const int yl = iy == 0 ? 0 : (PY == 0 ? 0 : (PY == 1 ? 1 : 2)), yh = iy == 0 ? 1 : (PY == 0 ? 1 : (PY == 1 ? 2 : 3));
         const int xl = ix == 0 ? 0 : (PX == 0 ? 0 : (PX == 1 ? 1 : 2)), xh = ix == 0 ? 1 : (PX == 0 ? 1 : (PX == 1 ? 2 : 3));
-        const float4 wa = tw[2 * smp], wb = tw[2 * smp + 1];          // (w1, w1, w2, w2), (w3, w3, w4, w4)
-        const float2 w1 = make_float2(wa.x, wa.y), w2 = make_float2(wa.z, wa.w);
-        const float2 w3 = make_float2(wb.x, wb.y), w4 = make_float2(wb.z, wb.w);
+        // one 16-byte table read per sample; the packed operands {w, w} are built in registers (a uniform LDS.128
+        // costs two L1 wavefronts, the busiest unit of this kernel, a register move costs an idle ALU slot)
+        const float4 wv = tw[smp];                                    // (w1, w2, w3, w4)
+        const float2 w1 = make_float2(wv.x, wv.x), w2 = make_float2(wv.y, wv.y);
+        const float2 w3 = make_float2(wv.z, wv.z), w4 = make_float2(wv.w, wv.w);
         const float4 v1 = G[yl][xl], v2 = G[yl][xh], v3 = G[yh][xl], v4 = G[yh][xh];
         if (EXACT) {
             // every product and every sum rounded once, in the reference's order; the sums are packed FFMA2 with an
@@ -719,8 +721,8 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
     const int opitch = (rows_per_cta * PW) | 1;
     const int obuf = (kChunk4 * opitch + 3) & ~3;                      // floats per output buffer, a multiple of 16 bytes
     float* ob = smem;                                                  // [128][opitch]
-    float4* tab_w = reinterpret_cast<float4*>(ob + obuf);              // [nbins][4 samples][2]: (w1,w1,w2,w2), (w3,w3,w4,w4)
-    int* s_bin = reinterpret_cast<int*>(tab_w + rows_per_cta * PW * 8);   // [nbins] ph | pw << 8 | pattern << 16
+    float4* tab_w = reinterpret_cast<float4*>(ob + obuf);              // [nbins][4 samples]: (w1, w2, w3, w4)
+    int* s_bin = reinterpret_cast<int*>(tab_w + rows_per_cta * PW * 4);   // [nbins] ph | pw << 8 | pattern << 16
 
     float r[5];
     load_roi(rois, k, p, r);
@@ -757,8 +759,7 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
         const bool ok = Y.valid && X.valid;
         const float w1 = ok ? __fmul_rn(Y.h, X.h) : 0.f, w2 = ok ? __fmul_rn(Y.h, X.l) : 0.f;
         const float w3 = ok ? __fmul_rn(Y.l, X.h) : 0.f, w4 = ok ? __fmul_rn(Y.l, X.l) : 0.f;
-        tab_w[2 * e] = make_float4(w1, w1, w2, w2);
-        tab_w[2 * e + 1] = make_float4(w3, w3, w4, w4);
+        tab_w[e] = make_float4(w1, w2, w3, w4);
     }
     __syncthreads();
     for (int b = tid; b < nbins; b += kRoiThreads) {
@@ -790,7 +791,7 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
             for (int b = warp; b < nbins; b += kRoiWarps) {
                 const int info = s_bin[b];
                 const uint4 ro4 = s_ro[info & 0xff], co4 = s_co[(info >> 8) & 0xff];
-                const float4* tw = tab_w + b * 8;
+                const float4* tw = tab_w + b * 4;
                 float4 av;
                 switch (info >> 16) {      // warp-uniform
                     case 0: av = bin_dedup<EXACT, 0, 0>(gp, ro4, co4, tw, ones); break;
@@ -979,7 +980,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
             const int nsplit = ceil_div(nbins, 112);
             const int rows = ceil_div(p.pooled_h, nsplit);
             const int band = rows * p.pooled_w;
-            const int smemd = ((kChunk4 * (band | 1) + 3) & ~3) * (int)sizeof(float) + band * 8 * 16 + band * 4;
+            const int smemd = ((kChunk4 * (band | 1) + 3) & ~3) * (int)sizeof(float) + band * 4 * 16 + band * 4;
             dim3 grid((unsigned)num_rois, (unsigned)ceil_div(p.pooled_h, rows));
             const float2 ones = make_float2(1.0f, 1.0f);
             static const int occ_env = getenv("MB_ROI_OCC") ? atoi(getenv("MB_ROI_OCC")) : 0;      // development switch

@@ -27,9 +27,11 @@ model = get_object_detection_model(3).eval().to(dev)
 with torch.no_grad():
     model.roi_heads.box_predictor.cls_score.weight.mul_(8.0)
 patch_model(model)
-g = torch.Generator(device=dev).manual_seed(0)
-mos = torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, device=dev, generator=g)
-tiles = len(mosaic.tile_grid(S, S, 1024, 128))
+grid = mosaic.tile_grid(S, S, 1024, 128)
+tiles = len(grid)
+y0, y1 = mosaic.rank_band(grid, 1024, S, world, rank)            # only this rank's pixel rows live on its GPU
+g = torch.Generator(device=dev).manual_seed(1 + rank)
+band = torch.randint(0, 256, (y1 - y0, S, 3), dtype=torch.uint8, device=dev, generator=g)
 
 
 def run():
@@ -37,18 +39,19 @@ def run():
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    b, s, l, crops = mosaic.infer_mosaic(model, mos, tile=1024, overlap=128, threshold=0.5, batch_size=4, rank=rank, world=world)
+    out = mosaic.infer_mosaic(model, band, (S, S), band_y0=y0, tile=1024, overlap=128, threshold=0.5, batch_size=4,
+                              rank=rank, world=world, crop_capacity_bytes=16 << 30)      # random-init weights on noise: large boxes
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    return time.perf_counter() - t0, b, crops
+    return time.perf_counter() - t0, out
 
 
 run()                                # warm-up (cuDNN autotune, lazy init)
-dt, b, crops = run()
+dt, out = run()
 if rank == 0:
-    nb = 0 if crops is None else int(crops.totals[1])
-    print(f"mosaic {S}x{S}: {tiles} tiles over {world} GPU(s): {dt * 1e3:.1f} ms ({tiles / dt:.0f} tiles/s), "
-          f"{b.shape[0]} detections after the seam NMS, rank-0 crop bytes {nb}")
+    kept = int((out["state"] == 1).sum())
+    print(f"mosaic {S}x{S}: {tiles} tiles over {world} GPU(s): {dt * 1e3:.1f} ms ({tiles / dt:.0f} tiles/s) including the "
+          f"backbone, {kept} detections after the seam NMS, rank-0 crops {out['crops']['count']} ({out['crops']['bytes']} bytes)")
 if world > 1:
     dist.destroy_process_group()

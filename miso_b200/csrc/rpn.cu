@@ -368,46 +368,81 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
     extern __shared__ unsigned long long keys[];
     __shared__ int run_off[MB_MAX_LEVELS + 1];
     __shared__ int wpre[MB_MAX_LEVELS][kSweepSmallMaxWords + 1];
+    __shared__ unsigned long long kword[MB_MAX_LEVELS][kSweepSmallMaxWords];      // the keep words themselves
+    __shared__ int s_cnt[MB_MAX_LEVELS], s_start[MB_MAX_LEVELS], s_T[MB_MAX_LEVELS];
     const int n = blockIdx.x, tid = threadIdx.x;
     const int Ktot = d.koff[d.L];
-    // per level: exclusive popcount prefix over the keep words, and the run offsets.
-    // One thread per (level, word) fetches and counts its word (independent loads, one latency), then one
-    // thread per level scans the counts in shared memory.
+    // per level: segment metadata, the keep words and their popcounts, staged in shared memory by one thread per
+    // (level, word) — one round of independent loads; everything after this reads global memory only for the
+    // scores and boxes of kept proposals
+    if (tid < d.L) {
+        const int g = n * d.L + tid;
+        s_cnt[tid] = w.seg.seg_count[g]; s_start[tid] = w.seg.seg_start[g]; s_T[tid] = w.seg.seg_words[g];
+    }
     {
         const int l = tid / (kSweepSmallMaxWords + 1), q = tid - l * (kSweepSmallMaxWords + 1);
-        if (l < d.L) {
+        if (l < d.L && q < kSweepSmallMaxWords) {
             const int g = n * d.L + l;
             const int T = w.seg.seg_words[g];
-            wpre[l][q] = (q < T) ? __popcll(w.keepbits[w.seg.keep_off[g] + q]) : 0;
+            const unsigned long long word = (q < T) ? w.keepbits[w.seg.keep_off[g] + q] : 0ull;
+            kword[l][q] = word;
+            wpre[l][q] = __popcll(word);
         }
     }
     __syncthreads();
-    if (tid < d.L) {
-        const int T = w.seg.seg_words[n * d.L + tid];
-        int acc = 0;
-        for (int q = 0; q < T; ++q) { const int c = wpre[tid][q]; wpre[tid][q] = acc; acc += c; }
-        wpre[tid][T] = acc;
+    {
+        // exclusive scan of a level's word counts by one warp (two words per lane, kSweepSmallMaxWords == 64)
+        const int l = tid >> 5, lane = tid & 31;
+        if (l < d.L) {
+            const int T = s_T[l];
+            const int c0 = lane < T ? wpre[l][lane] : 0, c1 = lane + 32 < T ? wpre[l][lane + 32] : 0;
+            int x0 = c0, x1 = c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+                if (lane >= o) { x0 += y0; x1 += y1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, x0, 31), tot1 = __shfl_sync(0xffffffffu, x1, 31);
+            if (lane < T) wpre[l][lane] = x0 - c0;
+            if (lane + 32 < T) wpre[l][lane + 32] = tot0 + x1 - c1;
+            if (lane == 0) wpre[l][T] = tot0 + tot1;
+        }
     }
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
-        for (int l = 0; l < d.L; ++l) { run_off[l] = acc; acc += wpre[l][w.seg.seg_words[n * d.L + l]]; }
+        for (int l = 0; l < d.L; ++l) { run_off[l] = acc; acc += wpre[l][s_T[l]]; }
         run_off[d.L] = acc;
     }
     __syncthreads();
     // one flat loop over the candidate slots of all levels (slot e of the image belongs to level l with
-    // koff[l] <= e < koff[l+1]): the dependent global loads of different levels overlap
-    for (int e = tid; e < Ktot; e += kRpnThreads) {
-        int l = 0;
-        while (l + 1 < d.L && e >= d.koff[l + 1]) ++l;
-        const int g = n * d.L + l, q = e - d.koff[l];
-        if (q >= w.seg.seg_count[g]) continue;
-        const unsigned long long word = w.keepbits[w.seg.keep_off[g] + (q >> 6)];
-        if ((word >> (q & 63)) & 1ull) {
-            const int j = wpre[l][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull));
-            const int p = w.seg.seg_start[g] + q;
-            keys[run_off[l] + j] = ((unsigned long long)desc_score_key(w.score[p]) << 32) | (unsigned int)(p - n * Ktot);
+    // koff[l] <= e < koff[l+1]); the kept test runs on shared memory, only kept slots load their score, and the
+    // loads of a thread's slots are independent of each other
+    for (int e0 = 0; e0 < Ktot; e0 += 4 * kRpnThreads) {
+        int pos[4], pp[4];
+        float sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * kRpnThreads + tid;
+            pos[u] = -1; pp[u] = 0;
+            if (e < Ktot) {
+                int l = 0;
+                while (l + 1 < d.L && e >= d.koff[l + 1]) ++l;
+                const int q = e - d.koff[l];
+                if (q < s_cnt[l]) {
+                    const unsigned long long word = kword[l][q >> 6];
+                    if ((word >> (q & 63)) & 1ull) {
+                        pos[u] = run_off[l] + wpre[l][q >> 6] + __popcll(word & ((1ull << (q & 63)) - 1ull));
+                        pp[u] = s_start[l] + q;
+                    }
+                }
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sc[u] = pos[u] >= 0 ? __ldg(w.score + pp[u]) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pos[u] >= 0) keys[pos[u]] = ((unsigned long long)desc_score_key(sc[u]) << 32) | (unsigned int)(pp[u] - n * Ktot);
     }
     __syncthreads();
     const int total = run_off[d.L];
@@ -415,7 +450,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, Rp
     for (int e = tid; e < total; e += kRpnThreads) {
         int l = 0;
         while (e >= run_off[l + 1]) ++l;
-        const int rank = merged_rank(keys, run_off, d.L, l, e - run_off[l]);
+        const int rank = merged_rank_capped(keys, run_off, d.L, l, e - run_off[l], nout);
         if (rank < nout) {
             const int p = n * Ktot + (int)(keys[e] & 0xffffffffull);
             proposals_out[(size_t)n * d.post_nms_top_n + rank] = w.rbox[p];

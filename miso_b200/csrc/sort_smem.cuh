@@ -107,4 +107,28 @@ __device__ __forceinline__ int merged_rank(const unsigned long long* keys, const
     return rank;
 }
 
+// merged_rank when only ranks below `cap` matter (top-cap of the merge): returns a value >= cap as soon as the rank is
+// known to reach it. Element j of its own run has rank >= j; in every other run at most cap - rank keys can still
+// precede it without pushing it out, so one probe at that position either ends the search or bounds it.
+__device__ __forceinline__ int merged_rank_capped(const unsigned long long* keys, const int* off, int S, int s, int j, int cap) {
+    if (j >= cap) return cap;
+    const unsigned long long key = keys[off[s] + j];
+    int rank = j;
+    for (int r = 0; r < S; ++r) {
+        if (r == s) continue;
+        const unsigned long long* run = keys + off[r];
+        const int len = off[r + 1] - off[r];
+        const int lim = min(len, cap - rank);                  // more than this many smaller keys -> rank >= cap
+        if (lim <= 0) return cap;
+        if (run[lim - 1] < key) {                              // at least lim keys of this run precede
+            if (lim == cap - rank) return cap;
+            rank += lim;                                       // lim == len: the whole run precedes
+            continue;
+        }
+        rank += lower_bound_smem(run, lim, key);
+        if (rank >= cap) return cap;
+    }
+    return rank;
+}
+
 }  // namespace mb

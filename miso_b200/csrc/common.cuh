@@ -1,5 +1,6 @@
 // common.cuh — shared device helpers for libmisob200 (sm_100a only).
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,6 +33,34 @@
     } while (0)
 
 namespace mb {
+
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// The per-batch path is a chain of ~16 short dependent kernels; launched back to back each boundary costs the full
+// drain + launch latency. Kernels of the chain begin with pdl_wait() (griddepcontrol.wait: returns once the preceding
+// grid has completed and its writes are visible) followed by pdl_trigger() (griddepcontrol.launch_dependents), and
+// are launched through launch_pdl() with programmatic stream serialization: the next grid's CTAs are scheduled while
+// the current one drains and sit at their pdl_wait(). Only kernels that start with pdl_wait() may be launched this
+// way; MB_PDL=0 turns the attribute off (A/B switch), the waits are then no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_wait(); pdl_trigger(); }
+
+inline bool pdl_enabled() {
+    static const bool v = [] { const char* e = getenv("MB_PDL"); return !(e != nullptr && e[0] == '0'); }();
+    return v;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // SM count of the current device (148 on a B200), asked once per device: grids are sized in multiples of it
 inline int num_sms() {

@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kDetThreads) k_det_candidates(const DetDev d, 
                                                                const float4* __restrict__ proposals,
                                                                const int* __restrict__ prop_counts, int packed,
                                                                DetScratch w) {
+    pdl_enter();
     const int t = blockIdx.x * kDetThreads + threadIdx.x;
     if (t >= d.N * d.max_props) return;
     const int n = t / d.max_props, r = t - n * d.max_props;
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kDetThreads) k_det_candidates(const DetDev d, 
 // word is written by two threads (no ordering between threads is assumed).
 __global__ void __launch_bounds__(256) k_det_init(int G, int max_props, long long seg_start_vec, uint4* __restrict__ zero16,
                                                   long long zero_vecs, int* __restrict__ bseg, long long P) {
+    pdl_enter();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
     const long long seg_vecs = ((long long)G + 3) / 4;
     for (long long j = i; j < zero_vecs; j += stride) {
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(kDetFinalThreads) k_det_finalize(const DetDev 
                                                                   float4* det_boxes, float4* det_boxes_net,
                                                                   float* det_scores, long long* det_labels,
                                                                   int* det_counts, int use_merge, int smem_keys) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned long long keys_smem[];
     unsigned long long* keys = keys_smem;
     __shared__ int s_cnt;
@@ -307,18 +310,14 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     if ((w.zero_bytes & 15) != 0 || (reinterpret_cast<uintptr_t>(workspace) & 15) != 0) return MB_ERR_INVALID_ARG;
     const size_t seg_start_off = (size_t)((const char*)w.seg.seg_start - (const char*)workspace);
     if ((seg_start_off & 15) != 0 || seg_start_off + 4 * (size_t)((G + 3) / 4 * 4) > w.zero_bytes) return MB_ERR_INVALID_ARG;
-    k_det_init<<<max(ceil_div(G, 256), 32), 256, 0, stream>>>(G, d.max_props, (long long)(seg_start_off / 16), (uint4*)workspace,
-                                                              (long long)(w.zero_bytes / 16), w.bseg, (long long)w.P);
-    MB_LAUNCH_CHECK();
-    k_det_candidates<<<ceil_div(d.N * d.max_props, kDetThreads), kDetThreads, 0, stream>>>(
-        d, im, class_logits, box_regression, (const float4*)proposals, prop_counts, packed, w);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_det_init, max(ceil_div(G, 256), 32), 256, 0, stream, G, d.max_props, (long long)(seg_start_off / 16),
+                       (uint4*)workspace, (long long)(w.zero_bytes / 16), w.bseg, (long long)w.P));
+    MB_CUDA(launch_pdl(k_det_candidates, ceil_div(d.N * d.max_props, kDetThreads), kDetThreads, 0, stream,
+                       d, im, class_logits, box_regression, (const float4*)proposals, prop_counts, packed, w));
     MetaRule rule{d.C - 1, 1, p->trick_numel, w.img_max, w.seg_offset};
-    k_seg_meta<<<1, 1024, 0, stream>>>(w.seg, G, 0, w.mask_words, rule);
-    MB_LAUNCH_CHECK();
-    k_rank_in_segment<<<(int)ceil_div64(w.P, kRankKeys), kRankThreads, 0, stream>>>(
-        w.bkey, w.bbox, w.bseg, w.seg.seg_start, w.seg.seg_count, nullptr, (int)w.P, w.skey, w.sbox);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_seg_meta, 1, 1024, 0, stream, w.seg, G, 0, w.mask_words, rule));
+    MB_CUDA(launch_pdl(k_rank_in_segment, (int)ceil_div64(w.P, kRankKeys), kRankThreads, 0, stream,
+                       w.bkey, w.bbox, w.bseg, w.seg.seg_start, w.seg.seg_count, nullptr, (int)w.P, w.skey, w.sbox));
     rc = launch_mask_and_sweep(w.sbox, w.seg, G, d.max_props, p->nms_thresh, w.mask, w.keepbits, d.dpi, stream, w.seg_offset);
     if (rc != MB_OK) return rc;
     const long long per_seg = d.max_props < d.dpi ? d.max_props : d.dpi;
@@ -328,8 +327,7 @@ extern "C" int mb_det_postprocess(const mb_det_params* p, const float* class_log
     if (cap > kDetSortCap) cap = kDetSortCap;                             // larger actual counts sort in w.gkeys
     const int smem = (cap > 2 ? cap : 2) * (int)sizeof(unsigned long long);
     MB_DYN_SMEM(k_det_finalize, smem);
-    k_det_finalize<<<d.N, kDetFinalThreads, smem, stream>>>(d, im, w, (float4*)det_boxes, (float4*)det_boxes_net, det_scores,
-                                                           (long long*)det_labels, det_counts, use_merge, cap);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_det_finalize, d.N, kDetFinalThreads, smem, stream, d, im, w, (float4*)det_boxes, (float4*)det_boxes_net,
+                       det_scores, (long long*)det_labels, det_counts, use_merge, cap));
     return MB_OK;
 }

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) k_mosaic_pack(const float4* __restrict__ 
                                                      const long long* __restrict__ det_labels, const int* __restrict__ det_counts,
                                                      const float2* __restrict__ origins_yx, int tiles, int dpi, float threshold,
                                                      int rows, float* __restrict__ block) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
     float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, -1.0f};
@@ -53,10 +54,9 @@ extern "C" int mb_mosaic_pack(const float* det_boxes, const float* det_scores, c
     if (tiles < 0 || dpi < 1 || rows < (int64_t)tiles * dpi || rows >= (1ll << 31)) return MB_ERR_INVALID_ARG;
     if (rows == 0) return MB_OK;
     if (!block_out || (tiles > 0 && (!det_boxes || !det_scores || !det_labels || !det_counts || !origins_yx))) return MB_ERR_INVALID_ARG;
-    mb::k_mosaic_pack<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(det_boxes), det_scores, reinterpret_cast<const long long*>(det_labels), det_counts,
-        reinterpret_cast<const float2*>(origins_yx), tiles, dpi, threshold, (int)rows, block_out);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(mb::launch_pdl(mb::k_mosaic_pack, (unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream,
+                           reinterpret_cast<const float4*>(det_boxes), det_scores, reinterpret_cast<const long long*>(det_labels),
+                           det_counts, reinterpret_cast<const float2*>(origins_yx), tiles, dpi, threshold, (int)rows, block_out));
     return MB_OK;
 }
 

@@ -100,6 +100,7 @@ struct MetaRule {
 
 static __global__ void __launch_bounds__(1024) k_seg_meta(SegArrays s, int G, int compute_starts,
                                                    long long mask_cap_words, MetaRule rule) {
+    pdl_enter();
     __shared__ long long sh[64];
     __shared__ long long carry[4];
     const int tid = threadIdx.x;
@@ -204,6 +205,7 @@ static __global__ void __launch_bounds__(kRankThreads) k_rank_in_segment(
     const int* __restrict__ bseg, const int* __restrict__ seg_start,
     const int* __restrict__ seg_count, const float* __restrict__ seg_offset, int P,
     unsigned long long* __restrict__ skey, float4* __restrict__ sbox) {
+    pdl_enter();
     __shared__ unsigned long long tile[kRankTile];
     __shared__ int s_lo, s_hi;
     const int tid = threadIdx.x, sub = tid % kRankSplit;
@@ -280,6 +282,7 @@ __device__ __forceinline__ float4 offset_box(float4 b, float o) {
 static __global__ void __launch_bounds__(128) k_nms_mask(const float4* __restrict__ sbox, SegArrays s, int G,
                                                  float thr_up, unsigned long long* __restrict__ mask,
                                                  const float* __restrict__ seg_offset, int full) {
+    pdl_enter();
     __shared__ float4 cbox[64];
     __shared__ float carea[64];
     // per-segment metadata of up to kMaskSegCache segments staged once per CTA: the tile -> (segment, row block, column
@@ -693,6 +696,7 @@ constexpr int kFixWords = kFixThreads / 64;
 
 static __global__ void __launch_bounds__(kFixThreads) k_nms_fixpoint(SegArrays s, const unsigned long long* __restrict__ mask,
                                                                      unsigned long long* __restrict__ keepbits, int max_keep) {
+    pdl_enter();
     __shared__ __align__(8) unsigned int C32[2 * kFixWords], R32[2 * kFixWords];
     const int g = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n = s.seg_count[g];
@@ -769,11 +773,9 @@ inline int launch_mask_and_sweep(const float4* sbox, SegArrays s, int G, int max
                                  cudaStream_t stream, const float* seg_offset = nullptr) {
     const float thr_up = strict_gt_threshold(iou_threshold);
     const bool fix = max_seg_elems <= kFixThreads && !sweep_in_order();
-    k_nms_mask<<<num_sms() * 16, 128, 0, stream>>>(sbox, s, G, thr_up, mask, seg_offset, fix ? 1 : 0);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_nms_mask, num_sms() * 16, 128, 0, stream, sbox, s, G, thr_up, mask, seg_offset, fix ? 1 : 0));
     if (fix) {
-        k_nms_fixpoint<<<G, kFixThreads, 0, stream>>>(s, mask, keepbits, max_keep);
-        MB_LAUNCH_CHECK();
+        MB_CUDA(launch_pdl(k_nms_fixpoint, G, kFixThreads, 0, stream, s, mask, keepbits, max_keep));
         return MB_OK;
     }
     // (the cp.async ring kernel below measured 8-12 % slower than this one at <= 4096 boxes, at every ring depth)

@@ -707,6 +707,7 @@ __global__ void __launch_bounds__(kRoiThreads, OCC) k_roi_align_nhwc4d(const mb_
                                                                    const float* __restrict__ rois,
                                                                    float* __restrict__ out, int* __restrict__ levels_out,
                                                                    int rows_per_cta, const float2 ones) {
+    pdl_enter();
     extern __shared__ __align__(16) float smem[];
     __shared__ Tap ytab[32], xtab[32];
     __shared__ uint4 s_ro[16], s_co[16];             // byte offsets of the distinct rows / columns of each bin row / column
@@ -987,7 +988,7 @@ extern "C" int mb_multiscale_roi_align(const mb_roi_align_params* pp, const floa
 #define MB_NHWC4D(E, O)                                                                                              \
     do {                                                                                                            \
         MB_DYN_SMEM((k_roi_align_nhwc4d<E, O>), smemd); \
-        k_roi_align_nhwc4d<E, O><<<grid, kRoiThreads, smemd, stream>>>(p, rois, out, levels_out, rows, ones);        \
+        MB_CUDA(launch_pdl((k_roi_align_nhwc4d<E, O>), grid, kRoiThreads, smemd, stream, p, rois, out, levels_out, rows, ones)); \
     } while (0)
             if (p.exact) { if (occ_env == 3) MB_NHWC4D(true, 3); else MB_NHWC4D(true, 4); }
             else MB_NHWC4D(false, 4);

@@ -111,6 +111,7 @@ __device__ __forceinline__ void block_to_level(const RpnDev& d, int b, int& n, i
 }
 
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_hist(const RpnDev d, RpnScratch w) {
+    pdl_enter();
     __shared__ int sh[kHistBins];
     __shared__ int s_last;
     int n, l, chunk;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_hist(const RpnDev d, RpnScr
 }
 
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnScratch w, long long* topk_idx_out) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned long long keys[];  // [kSelectSortCap]
     __shared__ int s_last, s_need, s_prefix_ok, s_single;
     __shared__ unsigned long long s_thr;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_select(const RpnDev d, RpnS
 
 // one CTA per (image, level): decode the winners in order, filter, compact
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_decode(const RpnDev d, const RpnImages im, RpnScratch w) {
+    pdl_enter();
     __shared__ int warp_cnt[32];
     __shared__ int s_base;
     const int g = blockIdx.x, n = g / d.L, l = g - n * d.L;
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(kRpnThreads) k_rpn_decode(const RpnDev d, cons
 // its index in its own list plus, per other level, a binary search — no sort.
 __global__ void __launch_bounds__(kRpnThreads) k_rpn_finalize(const RpnDev d, RpnScratch w, float4* proposals_out,
                                                              float* scores_out, int* counts_out, int sort_cap) {
+    pdl_enter();
     extern __shared__ unsigned long long keys[];
     __shared__ int run_off[MB_MAX_LEVELS + 1];
     __shared__ int wpre[MB_MAX_LEVELS][kSweepSmallMaxWords + 1];
@@ -525,17 +529,13 @@ extern "C" int mb_rpn_proposals(const mb_rpn_params* p, float* proposals_out, fl
     const int G = d.N * d.L;
     MB_CUDA(cudaMemsetAsync(workspace, 0, w.zero_bytes, stream));
     const int stream_blocks = d.N * d.boff[d.L];
-    k_rpn_hist<<<stream_blocks, kRpnThreads, 0, stream>>>(d, w);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_rpn_hist, stream_blocks, kRpnThreads, 0, stream, d, w));
     const int sel_smem = kSelectSortCap * (int)sizeof(unsigned long long);
     MB_DYN_SMEM(k_rpn_select, sel_smem);
-    k_rpn_select<<<stream_blocks, kRpnThreads, sel_smem, stream>>>(d, w, (long long*)topk_idx_out);
-    MB_LAUNCH_CHECK();
-    k_rpn_decode<<<G, kRpnThreads, 0, stream>>>(d, im, w);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_rpn_select, stream_blocks, kRpnThreads, sel_smem, stream, d, w, (long long*)topk_idx_out));
+    MB_CUDA(launch_pdl(k_rpn_decode, G, kRpnThreads, 0, stream, d, im, w));
     MetaRule rule{d.L, 0, p->trick_numel, w.img_max, w.seg_offset};
-    k_seg_meta<<<1, 1024, 0, stream>>>(w.seg, G, 0, w.mask_words, rule);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_seg_meta, 1, 1024, 0, stream, w.seg, G, 0, w.mask_words, rule));
     int max_k = 0;
     for (int l = 0; l < d.L; ++l) max_k = max_k > d.k[l] ? max_k : d.k[l];
     rc = launch_mask_and_sweep(w.rbox, w.seg, G, max_k, p->nms_thresh, w.mask, w.keepbits, d.post_nms_top_n, stream,
@@ -544,7 +544,6 @@ extern "C" int mb_rpn_proposals(const mb_rpn_params* p, float* proposals_out, fl
     const int cap = next_pow2(d.koff[d.L] > 2 ? d.koff[d.L] : 2);
     const int fin_smem = cap * (int)sizeof(unsigned long long);
     MB_DYN_SMEM(k_rpn_finalize, fin_smem);
-    k_rpn_finalize<<<d.N, kRpnThreads, fin_smem, stream>>>(d, w, (float4*)proposals_out, scores_out, counts_out, cap);
-    MB_LAUNCH_CHECK();
+    MB_CUDA(launch_pdl(k_rpn_finalize, d.N, kRpnThreads, fin_smem, stream, d, w, (float4*)proposals_out, scores_out, counts_out, cap));
     return MB_OK;
 }

@@ -240,24 +240,43 @@ __device__ __forceinline__ void crop_rows(const unsigned char* __restrict__ im, 
                                           int img_w, int ch, int row_bytes, int y0, int ystep, int lane) {
     constexpr int RPP = 32 / GS;
     const int gl = lane % GS, grp = lane / GS;
-    for (int y = y0 * RPP + grp; y < rc.w; y += ystep * RPP) {
-        const unsigned char* s = im + ((size_t)(rc.y + y) * img_w + rc.x) * ch;
-        unsigned char* o = dst + (size_t)y * row_bytes;
-        const int head = min(row_bytes, (int)((16 - (reinterpret_cast<uintptr_t>(o) & 15)) & 15));
+    // a vector's aligned 16- or 32-byte source window may reach past the crop's columns but must stay inside the
+    // image row: only crops within 16 bytes of the left or 32 bytes of the right image edge need the per-row check
+    const bool near_edge = rc.x * ch < 16 || (img_w - rc.x - rc.z) * ch < 32;
+    const int y_first = y0 * RPP + grp;
+    const size_t src_pitch = (size_t)img_w * ch;
+    const unsigned char* s = im + ((size_t)(rc.y + y_first) * img_w + rc.x) * ch;
+    unsigned char* o = dst + (size_t)y_first * row_bytes;
+    const size_t s_step = (size_t)ystep * RPP * src_pitch, o_step = (size_t)ystep * RPP * row_bytes;
+    for (int y = y_first; y < rc.w; y += ystep * RPP, s += s_step, o += o_step) {
+        const int head = min(row_bytes, (int)((16u - ((unsigned)reinterpret_cast<uintptr_t>(o) & 15u)) & 15u));
         const unsigned char* sv = s + head;
-        const int sh = (int)(reinterpret_cast<uintptr_t>(sv) & 15);
+        const int sh = (int)((unsigned)reinterpret_cast<uintptr_t>(sv) & 15u);
         const unsigned char* sa = sv - sh;
         const int nvec = (row_bytes - head) >> 4;
-        // a vector's aligned 16- or 32-byte source window may reach past the crop's columns but must stay inside the
-        // image row [row_lo, row_hi): only crops touching the left / right image edge lose vectors to the byte path
-        const unsigned char* row_lo = s - (size_t)rc.x * ch;
-        const long long before = sa - row_lo;                          // < 0: vector 0's window starts left of the image row
-        const long long after = (row_lo + (size_t)img_w * ch) - sa;    // bytes from sa to the end of the image row
-        const int i0 = before < 0 ? 1 : 0;
-        const long long fit = (after - (sh != 0 ? 32 : 16)) >> 4;      // last vector index whose window ends inside the row
-        const int nsafe = fit < 0 ? 0 : (int)min((long long)nvec, fit + 1);
+        int i0 = 0, nsafe = nvec;
+        if (near_edge) {
+            const unsigned char* row_lo = s - (size_t)rc.x * ch;
+            const long long before = sa - row_lo;                          // < 0: vector 0's window starts left of the image row
+            const long long after = (row_lo + src_pitch) - sa;             // bytes from sa to the end of the image row
+            i0 = before < 0 ? 1 : 0;
+            const long long fit = (after - (sh != 0 ? 32 : 16)) >> 4;      // last vector index whose window ends inside the row
+            nsafe = fit < 0 ? 0 : (int)min((long long)nvec, fit + 1);
+        }
         const int ws = sh >> 2;
         const unsigned bs = (unsigned)(sh & 3) * 8u;
+        // bytes the vectors do not cover: [0, head + 16 * i0) and [head + 16 * max(nsafe, i0), row_bytes). Their loads
+        // (two per lane cover the usual <= 30 bytes) are issued before the vector loop so that both kinds of load
+        // share one memory latency; the rest, if any, follows in a loop.
+        const int lo_end = min(row_bytes, head + 16 * i0);
+        const int hi_begin = min(row_bytes, max(lo_end, head + 16 * max(nsafe, i0)));
+        const int nbyte = lo_end + (row_bytes - hi_begin);
+        const int q0 = gl, q1 = gl + GS;
+        const int bi0 = q0 < lo_end ? q0 : hi_begin + (q0 - lo_end), bi1 = q1 < lo_end ? q1 : hi_begin + (q1 - lo_end);
+        unsigned char byte0 = 0, byte1 = 0;
+        if (q0 < nbyte) byte0 = __ldg(s + bi0);
+        if (q1 < nbyte) byte1 = __ldg(s + bi1);
+#pragma unroll 2
         for (int i = i0 + gl; i < nsafe; i += GS) {
             const uint4 a = ldg128(sa + 16 * i);
             uint4 b = make_uint4(0u, 0u, 0u, 0u);
@@ -270,18 +289,16 @@ __device__ __forceinline__ void crop_rows(const unsigned char* __restrict__ im, 
             r.z = __funnelshift_r(w2, w3, bs); r.w = __funnelshift_r(w3, w4, bs);
             *reinterpret_cast<uint4*>(o + head + 16 * i) = r;
         }
-        // bytes the vectors did not cover: [0, head + 16 * i0) and [head + 16 * max(nsafe, i0), row_bytes), as one loop
-        const int lo_end = min(row_bytes, head + 16 * i0);
-        const int hi_begin = min(row_bytes, max(lo_end, head + 16 * max(nsafe, i0)));
-        const int nbyte = lo_end + (row_bytes - hi_begin);
-        for (int q = gl; q < nbyte; q += GS) {
+        if (q0 < nbyte) o[bi0] = byte0;
+        if (q1 < nbyte) o[bi1] = byte1;
+        for (int q = gl + 2 * GS; q < nbyte; q += GS) {
             const int bidx = q < lo_end ? q : hi_begin + (q - lo_end);
             o[bidx] = __ldg(s + bidx);
         }
     }
 }
 
-__global__ void __launch_bounds__(256, 6) k_crop_gather(const CropDev d, const int4* __restrict__ rects,
+__global__ void __launch_bounds__(256, 5) k_crop_gather(const CropDev d, const int4* __restrict__ rects,
                                                     const int* __restrict__ src, const long long* __restrict__ offsets,
                                                     long long* __restrict__ totals, unsigned char* __restrict__ out,
                                                     long long capacity) {
@@ -299,8 +316,9 @@ __global__ void __launch_bounds__(256, 6) k_crop_gather(const CropDev d, const i
         const unsigned char* im = d.img[n];
         unsigned char* dst = out + offsets[j];
         // lanes per row by the row length (warp-uniform: every warp of the CTA works on crop j)
-        if (row_bytes <= 8 * 16 + 15) crop_rows<8>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);
-        else if (row_bytes <= 16 * 16 + 15) crop_rows<16>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);
+        // (two vectors per lane: more rows of a crop in flight per warp, and the loop unrolls to both loads first)
+        if (row_bytes <= 16 * 16 + 15) crop_rows<8>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);
+        else if (row_bytes <= 32 * 16 + 15) crop_rows<16>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);
         else crop_rows<32>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);
     }
 }

@@ -115,8 +115,14 @@ def forward_uint8(model, images_u8: List[Tensor]):
     from torchvision.models.detection.image_list import ImageList
     tr = model.transform
     original_image_sizes = [(int(im.shape[0]), int(im.shape[1])) for im in images_u8]
-    batch, sizes = ops.transform_images(images_u8, tr.min_size[-1], tr.max_size, tr.image_mean, tr.image_std, tr.size_divisible)
-    images = ImageList(batch, sizes)
+    if getattr(tr, "fixed_size", None) is not None or getattr(tr, "_skip_resize", False):
+        # the fused kernel implements the min_size / max_size rule only; the other two modes of
+        # GeneralizedRCNNTransform (tv:models/detection/transform.py:160-183) run through the model's own transform
+        # (torch ops on the device), so the result stays the reference's
+        images, _ = tr([im.permute(2, 0, 1).to(torch.float32) / 255 for im in images_u8])
+    else:
+        batch, sizes = ops.transform_images(images_u8, tr.min_size[-1], tr.max_size, tr.image_mean, tr.image_std, tr.size_divisible)
+        images = ImageList(batch, sizes)
     features = model.backbone(images.tensors)
     if isinstance(features, Tensor):
         features = {"0": features}

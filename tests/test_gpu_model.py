@@ -213,6 +213,27 @@ def test_forward_uint8_equals_float_forward():
         assert torch.equal(x["boxes"], y["boxes"]) and torch.equal(x["labels"], y["labels"]) and torch.equal(x["scores"], y["scores"])
 
 
+def test_forward_uint8_fixed_size_and_skip_resize_follow_the_models_transform():
+    """GeneralizedRCNNTransform's other two modes (fixed_size, _skip_resize) are not what the fused transform kernel
+    implements: forward_uint8 must hand those to the model's own transform and return what model(float images)
+    returns."""
+    from miso_b200.patch import forward_uint8, patch_model
+    model = patch_model(make_model("faster").to(DEV))
+    g = torch.Generator().manual_seed(9)
+    u8 = [torch.randint(0, 256, (320, 384, 3), dtype=torch.uint8, generator=g).to(DEV) for _ in range(2)]
+    fl = [x.permute(2, 0, 1).to(torch.float32) / 255 for x in u8]
+    for attr, value in (("fixed_size", (352, 416)), ("_skip_resize", True)):
+        old = getattr(model.transform, attr, None)
+        setattr(model.transform, attr, value)
+        try:
+            with torch.inference_mode():
+                a, b = forward_uint8(model, u8), model(fl)
+        finally:
+            setattr(model.transform, attr, old)
+        for x, y in zip(a, b):
+            assert torch.equal(x["boxes"], y["boxes"]) and torch.equal(x["labels"], y["labels"]) and torch.equal(x["scores"], y["scores"])
+
+
 def test_dispatcher_override_routes_torchvision_ops():
     import torchvision
     from miso_b200.patch import override_torchvision_ops

@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4, help="tiles per batch (4 = BASELINE config 2's batch)")
+    ap.add_argument("--batch", type=int, default=8, help="tiles per batch (each tile has BASELINE config 2's per-image shape; 4 = config 2's batch)")
     ap.add_argument("--mosaic", type=int, default=16384, help="mosaic side in pixels (16384 = BASELINE config 5)")
     ap.add_argument("--fast-roi-align", action="store_true", help="FMA RoIAlign (<=1e-5) instead of the bit-exact order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -657,7 +657,9 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "roi_align_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get(roi_kernel, {}).get("dram_bytes_per_launch")
+            entry = json.load(fh).get(roi_kernel, {})
+            # captured per launch size (tiles per batch); a size without its own capture reports null, not a scaled guess
+            traffic = entry.get("dram_bytes_per_launch_by_tiles", {}).get(str(args.batch), entry.get("dram_bytes_per_launch") if args.batch == 4 else None)
     # aggregate: RoIAlign bytes + RPN (objectness scan 2x4 B/anchor + 36 B per decoded winner) + detection
     # post-processing (4*R*5C in + 24 B/det) per tile, pack/unpack + seam rows (24 B each, read twice), crops read+write
     n_anchor = sum(3 * gh * gw for gh, gw in sh.rpn_grids)
@@ -668,9 +670,9 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": w.name, "tiles": T, "tiles_rank0": len(mine), "tiles_per_batch": args.batch,
-                   "batch_shape": "BASELINE config 2 per batch (4 x 1024^2 -> 800^2, 1000 proposals, 256 ch, 7x7, 300 dets)",
+                   "batch_shape": f"{args.batch} tiles per batch, each with BASELINE config 2's per-image shape (1024^2 -> 800^2, 1000 proposals, 256 ch, 7x7, 300 dets)",
                    "features_layout": args.features_layout,
-                   "l2": f"inputs larger than L2: every batch has its own {4 * w.bytes_per_tile() / 1e6:.0f} MB of inputs ({len(mine) * w.bytes_per_tile() / 1e9:.1f} GB resident on rank 0) + 201 MB RoIAlign output",
+                   "l2": f"inputs larger than L2: every batch has its own {args.batch * w.bytes_per_tile() / 1e6:.0f} MB of inputs ({len(mine) * w.bytes_per_tile() / 1e9:.1f} GB resident on rank 0) + {args.batch * 50.2:.0f} MB RoIAlign output",
                    "roi_align_mode": "fast(fma)" if args.fast_roi_align else "exact(reference op order)",
                    "multi_gpu": (f"strong scaling: contiguous tile blocks per rank, one NCCL all_gather_into_tensor of [{plan.block_rows}, 6] rows per rank, "
                                  "sparse seam NMS replicated on every rank, crops cut by the rank that owns the source tile") if world > 1 else "single GPU",

@@ -16,7 +16,7 @@ from tests.test_gpu_seam import seam_block  # noqa: E402
 
 DEV = "cuda:0"
 rng = np.random.default_rng(0)
-n = 4
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 4          # images (tiles) per launch
 feats = [torch.randn(n, 256, 800 // s, 800 // s, device=DEV).contiguous(memory_format=torch.channels_last) for s in (4, 8, 16, 32)]
 boxes = [torch.from_numpy(cases.stress_rois(rng, 1000, (800, 800))).to(DEV) for _ in range(n)]
 x = {str(i): f for i, f in enumerate(feats)}

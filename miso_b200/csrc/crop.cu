@@ -309,12 +309,20 @@ __global__ void __launch_bounds__(256, 5) k_crop_gather(const CropDev d, const i
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int y0 = blockIdx.y * nwarps + warp, ystep = gridDim.y * nwarps;
+    // the next crop's rectangle, source slot and offset are fetched while the current crop is copied: a crop then costs
+    // one memory latency (its rows), not two
+    int4 rc_next = make_int4(0, 0, 0, 0);
+    int src_next = 0;
+    long long off_next = 0;
+    if ((long long)blockIdx.x < ncrops) { rc_next = rects[blockIdx.x]; src_next = src[blockIdx.x]; off_next = offsets[blockIdx.x]; }
     for (long long j = blockIdx.x; j < ncrops; j += gridDim.x) {
-        const int4 rc = rects[j];
-        const int n = src[j] / d.cap;
+        const int4 rc = rc_next;
+        const int n = src_next / d.cap;
+        unsigned char* dst = out + off_next;
+        const long long jn = j + gridDim.x;
+        if (jn < ncrops) { rc_next = rects[jn]; src_next = src[jn]; off_next = offsets[jn]; }
         const int row_bytes = rc.z * d.ch;
         const unsigned char* im = d.img[n];
-        unsigned char* dst = out + offsets[j];
         // lanes per row by the row length (warp-uniform: every warp of the CTA works on crop j)
         // (two vectors per lane: more rows of a crop in flight per warp, and the loop unrolls to both loads first)
         if (row_bytes <= 16 * 16 + 15) crop_rows<8>(im, dst, rc, d.w[n], d.ch, row_bytes, y0, ystep, lane);

@@ -143,24 +143,37 @@ __global__ void __launch_bounds__(1024) k_seam_pairs(const float* __restrict__ b
         auto process = [&]() {
             const int n = s_n;
             if (mine) {
-                for (int i = 0; i < n; ++i) {
-                    const SeamCand c = cand[i];
-                    if (c.label != mlabel) continue;
-                    if (!(c.key < mkey || (c.key == mkey && c.row < my_row))) continue;      // c must precede me
-                    // disjoint boxes have IoU 0 (or NaN for two zero-area boxes): never > thr >= 0; skip the division
-                    if (c.box.z < mb_.x || mb_.z < c.box.x || c.box.w < mb_.y || mb_.w < c.box.y) continue;
-                    if (!iou_suppresses(c.box, c.area, mb_, marea, thr_up)) continue;
-                    if (pass == 0) {
+                // 32 candidates at a time. Pass A marks the ones that pass the cheap tests (same label, precedes me,
+                // boxes not disjoint — disjoint boxes have IoU 0, or NaN for two zero-area boxes: never > thr >= 0) without
+                // branching; pass B runs the exact IoU on the few marked ones, each lane walking its own bits. In one
+                // loop a warp paid for the division whenever any of its 32 rows passed the cheap tests.
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int m1 = min(32, n - i0);
+                    unsigned int hit = 0;
+#pragma unroll 4
+                    for (int k = 0; k < m1; ++k) {
+                        const SeamCand c = cand[i0 + k];
+                        const bool pre = c.key < mkey || (c.key == mkey && c.row < my_row);      // c must precede me
+                        const bool apart = c.box.z < mb_.x || mb_.z < c.box.x || c.box.w < mb_.y || mb_.w < c.box.y;
+                        if (c.label == mlabel && pre && !apart) hit |= 1u << k;
+                    }
+                    while (hit) {
+                        const int k = __ffs((int)hit) - 1;
+                        hit &= hit - 1u;
+                        const SeamCand c = cand[i0 + k];
+                        if (!iou_suppresses(c.box, c.area, mb_, marea, thr_up)) continue;
+                        if (pass == 0) {
 #pragma unroll
-                        for (int e = 0; e < kSeamRegEdges; ++e)
-                            if (my_count == e) reg_e[e] = c.row;
-                        ++my_count;
-                    } else {
-                        // the neighbour list's order may differ between the passes, so a row that overflowed its
-                        // registers rewrites its whole segment
-                        const int slot = my_off + seen;
-                        if (my_count > kSeamRegEdges && slot < edge_cap) w.edges[slot] = make_int2(c.row, my_row);
-                        ++seen;
+                            for (int e = 0; e < kSeamRegEdges; ++e)
+                                if (my_count == e) reg_e[e] = c.row;
+                            ++my_count;
+                        } else {
+                            // the neighbour list's order may differ between the passes, so a row that overflowed its
+                            // registers rewrites its whole segment
+                            const int slot = my_off + seen;
+                            if (my_count > kSeamRegEdges && slot < edge_cap) w.edges[slot] = make_int2(c.row, my_row);
+                            ++seen;
+                        }
                     }
                 }
             }

@@ -450,11 +450,7 @@ extern "C" int mb_seam_nms(const float* block, int64_t rows, int32_t rows_per_ti
     MB_LAUNCH_CHECK();
     const int threads = ((rows_per_tile + 31) / 32) * 32;
     const int pair_smem = kSeamChunk * (int)sizeof(SeamCand);
-    static bool attr = false;
-    if (!attr) {
-        MB_DYN_SMEM(k_seam_pairs, pair_smem);
-        attr = true;
-    }
+    MB_DYN_SMEM(k_seam_pairs, pair_smem);
     k_seam_pairs<<<tiles, threads, pair_smem, stream>>>(block, (int)rows, rows_per_tile, tiles, thr_up, w, (int)edge_capacity);
     MB_LAUNCH_CHECK();
     const int flag_smem = rows_per_tile * (int)sizeof(int);

@@ -6,9 +6,10 @@
 
 Workload (every N, strong scaling): BASELINE.json config 5 — ONE 16384x16384 synthetic mosaic cut into 361 tiles
 of 1024 px with 128 px overlap, partitioned over the N ranks in contiguous blocks. A "step" is one pass over the
-whole mosaic: every rank runs its tiles through the post-head path in batches of 4 tiles — each batch is exactly
-BASELINE config 2 (batch 4, 1024^2 -> 800^2, 1000 RPN proposals/image, 256-channel pyramid, RoIAlign 7x7, 300
-detections/image): RPN post-head stage -> MultiScaleRoIAlign -> detection post-processing -> pack — then ONE
+whole mosaic: every rank runs its tiles through the post-head path in batches of 8 tiles (--batch; 4 is exactly
+BASELINE config 2's batch) — every tile has config 2's per-image shape (1024^2 -> 800^2, 1000 RPN proposals/image,
+256-channel pyramid, RoIAlign 7x7, 300 detections/image): RPN post-head stage -> MultiScaleRoIAlign -> detection
+post-processing -> pack — then ONE
 NCCL all-gather of the per-rank detection blocks, the seam NMS over all 108 300 gathered rows and the crops of the
 rank's own surviving detections from its pixel band. The CNN parts (backbone, RPN head, box head) are not on
 this path; their outputs are seeded random tensors (a function of the tile index, so every world size sees the
@@ -22,8 +23,9 @@ same tiles). All inputs are resident in HBM (22 GB at N=1) when the timed region
             gathered rows, the seam-NMS keep set and its own crops (rectangles + bytes) are identical; N=1 — the
             keep set against torchvision's CPU _batched_nms_vanilla on the same 108 300 rows and sampled crops
             against numpy slices.
-  roofline  RoIAlign (k_roi_geom + k_roi_align_tma): exact algorithmic bytes of every launch (union
-            of touched pixels rasterised on the GPU) / CUDA-event duration, over all launches of the timed region.
+  roofline  RoIAlign (k_roi_align_nhwc4d, the default route; the opt-in TMA route is timed beside it): exact
+            algorithmic bytes of every launch (union of touched pixels rasterised on the GPU) /
+            CUDA-event duration, over all launches of the timed region.
   aggregate Σ stage bytes / step time for the rank's whole step.
   e2e       the same job through miso_b200.mosaic.HostMosaicRunner: every batch's inputs come from pinned HOST
             memory (H2D inside the timed region), results (bounds, rectangles, crop bytes) return to pinned host.

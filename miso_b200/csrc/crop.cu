@@ -8,8 +8,10 @@
 //
 //   k_crop_plan    one CTA: filter + rounding + slice resolution + stable compaction + byte offsets
 //   k_crop_plan_chunks  the same for many slots (mosaic rows): CTA per 4096 slots, chained by flagged aggregates
-//   k_crop_gather  persistent grid (SM-count multiple): crop slots strided over blockIdx.x, rows over
-//                  blockIdx.y, lanes along the contiguous bytes of a source row (HWC uint8)
+//   k_crop_gather  persistent grid (SM-count multiple): crop slots strided over blockIdx.x (the next slot's metadata
+//                  prefetched), rows over the CTA's warps and blockIdx.y, 8 / 16 / 32 lanes per row by row length;
+//                  a row moves as 16-byte destination vectors assembled from two aligned source vectors (word
+//                  select + funnel shift), bytes only at its unaligned ends and at the image border (HWC uint8)
 #include <math.h>
 
 #include <algorithm>

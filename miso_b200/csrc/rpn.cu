@@ -8,14 +8,18 @@
 //                  (warp-aggregated shared-memory atomics); the last CTA of each (image, level)
 //                  finds the bin that holds the k-th largest logit          [radix-select pass 1]
 //   k_rpn_select   second coalesced pass over the logits: keys above the threshold bin are
-//                  taken, keys inside it become candidates; the last CTA of each (image, level)
-//                  resolves the candidates (remaining key bits + index) and bitonic-sorts the k
-//                  winners in shared memory -> (logit desc, anchor index asc)  [pass 2 + sort]
+//                  taken, keys inside it become candidates (one global atomic per CTA and list);
+//                  the last CTA of each (image, level) stages the candidates in shared memory,
+//                  resolves them (remaining key bits + index, 8 bits per pass, stopping as soon as
+//                  one candidate is left under the prefix) and bitonic-sorts the k winners in
+//                  shared memory -> (logit desc, anchor index asc)            [pass 2 + sort]
 //   k_rpn_decode   one CTA per (image, level): regenerate the anchor analytically, gather the 4
 //                  deltas from NCHW, decode, clip, small-box and score filters, stable compaction
-//   k_seg_meta / k_nms_mask / k_nms_sweep  (nms_core.cuh), segments = (image, level)
+//   k_seg_meta / k_nms_mask / k_nms_fixpoint  (nms_core.cuh), segments = (image, level)
 //   k_rpn_finalize one CTA per image: merge the kept boxes of all levels by (score desc, candidate
-//                  order asc), keep post_nms_top_n
+//                  order asc), keep post_nms_top_n (ranks computed only as far as that cut needs)
+// The kernels of the chain start with pdl_enter() and are launched with programmatic stream
+// serialization (common.cuh): the next kernel's launch overlaps the drain of the current one.
 // Only the selected anchors are decoded: 0.64 MB of logits + 4507*16 B of deltas per image are
 // read instead of the reference's 36 B x 159 882 anchors.
 #include <math.h>

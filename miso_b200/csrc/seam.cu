@@ -6,16 +6,18 @@
 // (tv-csrc:ops/cpu/nms_kernel.cpp:116, SURVEY.md Appendix B.1: fp32 IoU with one rounding per operation,
 // `(double)iou > thr`, candidates in stable descending-score order).
 //
-// The dense formulation (mb_nms mode 1: an n x n/64 bit matrix per label) costs 8.4 ms for the 108 300 rows of
+// The dense formulation (mb_nms mode 1: an n x n/64 bit matrix per label) costs 13.6 ms for the 108 300 rows of
 // a 16384^2 mosaic although almost every pair is disjoint: rows come in groups of `rows_per_tile` consecutive
 // rows (one tile's detections) and two rows can only interact if their boxes intersect. Greedy NMS is the
 // unique fixed point of   kept(j) <=> no kept i precedes j with same label and IoU(i, j) > thr,   so it can be
 // solved on the sparse "i may suppress j" graph:
 //   k_seam_prep     per tile: bounding box of its live rows (label >= 0), live count
-//   k_seam_pairs    CTA = tile t. Candidates = live rows of every tile whose bounding box intersects t's that
-//                   themselves intersect t's bounding box, compacted into shared memory; thread = own row j tests
-//                   them with the exact IoU predicate. Two passes (count, reserve one edge segment per tile
-//                   with one atomic, fill): no capacity guess per row.
+//   k_seam_pairs    CTA = tile t. The neighbour tiles (bounding box intersects t's) are found by all threads in
+//                   parallel; their live rows that intersect t's bounding box are compacted into shared memory;
+//                   thread = own row j tests them 32 at a time: cheap tests (label, precedence, boxes not disjoint)
+//                   without branching, then the exact IoU predicate on the lane's own marked candidates. The first
+//                   four suppressors of a row stay in registers, one edge segment per tile is reserved with one
+//                   atomic; a second pass over the candidates runs only for rows with more: no capacity guess per row.
 //   k_seam_resolve  CTA = tile. Rounds of: every edge (i -> j) with j undecided looks at state[i]
 //                   (kept -> j removed, undecided -> j blocked); undecided rows that are neither become kept.
 //                   Decisions are final and order-independent, so tiles run asynchronously on global state;
